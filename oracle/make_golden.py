@@ -1,0 +1,170 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* from the REAL reference closures.
+
+Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Every fixture stores the inputs that cannot be regenerated from a seed, the evaluation points q, and
+the reference closure's log-probability and gradient at each q (fp32, produced by the reference's own
+``define_model_log_prob`` + ``torch.autograd.grad``).  Large deterministic inputs (DeepONet data and
+VI artefacts) are NOT stored; they are regenerated from ``vihmc.synth`` with the recorded seeds.
+Also writes the bundled BNN regression data (data, not code) into the product package.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vi-hmc_b200"))
+
+from oracle import ref_loader  # noqa: E402
+from vihmc import synth  # noqa: E402
+from vihmc.spec import DeepONetArch  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _grad(closure, q):
+    p = q.detach().clone().requires_grad_()
+    lp = closure(p)
+    (g,) = torch.autograd.grad(lp.sum(), p)
+    return float(lp.sum()), g.detach().numpy().copy()
+
+
+def _write_artifacts(tmp, uid, mu, sigma, ind):
+    torch.save(mu, os.path.join(tmp, f"means_flattened_{uid}"))
+    torch.save(sigma, os.path.join(tmp, f"stds_flattened_{uid}"))
+    np.save(os.path.join(tmp, f"gradient_indices_{uid}.npy"), ind)
+
+
+def bnn_data_file():
+    x_tr, y_tr, x_va, y_va = ref_loader.load_bnn_data()
+    out = os.path.join(ROOT, "vi-hmc_b200", "vihmc", "data", "bnn_regression.npz")
+    np.savez(out, x_train=x_tr.numpy(), y_train=y_tr.numpy(), x_val=x_va.numpy(), y_val=y_va.numpy())
+    print("wrote", out)
+
+
+def bnn_vi_hmc_cases():
+    """Reference closure Neural_network/VI_HMC/main_VI_HMC.py:28-153 on the bundled data."""
+    m = ref_loader.load_bnn_vi_hmc()
+    cfg = m.cfg
+    x_tr, y_tr, _, _ = ref_loader.load_bnn_data()
+    cases = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg.prior_file, cfg.prior_uid = tmp, "synthetic"
+        for name, d, loss, tau_out, act, load_prior in [
+            ("d40_nll", 40, "NLL", 0.0025, "tanh", False),
+            ("d141_nll", 141, "NLL", 0.0025, "tanh", False),
+            ("d14_nll", 14, "NLL", 0.0025, "tanh", False),
+            ("d70_regression", 70, "regression", 400.0, "tanh", False),
+            ("d40_relu", 40, "NLL", 0.0025, "relu", False),
+            ("d40_sine", 40, "NLL", 0.0025, "sine", False),
+            ("d40_loadprior", 40, "NLL", 0.0025, "tanh", True),
+        ]:
+            mu, sigma, ind = synth.bnn_vi_artifacts(141, d, seed=1)
+            _write_artifacts(tmp, "synthetic", mu, sigma, ind)
+            cfg.act, cfg.load_prior, cfg.loss, cfg.tau_out = act, load_prior, loss, tau_out
+            torch.manual_seed(0)
+            net = m.get_model(cfg.bias)
+            shapes = [w.shape for w in net.parameters()]
+            numels = [w.nelement() for w in net.parameters()]
+            if load_prior:
+                prior_list = [mu[ind], sigma[ind]]
+            else:
+                prior_list = [torch.tensor(cfg.prior_var) for _ in numels]
+            closure = m.define_model_log_prob(net, loss, x_tr, y_tr, numels, shapes, prior_list, tau_out,
+                                              device="cpu", dt_string="golden")
+            rs = np.random.RandomState(100 + d)
+            qs = (mu.numpy()[ind][None, :] + sigma.numpy()[ind][None, :] * rs.randn(6, d)).astype(np.float32)
+            qs[5] = (0.7 * rs.randn(d)).astype(np.float32)  # one far-from-mode point
+            lps, grads = zip(*[_grad(closure, torch.from_numpy(q)) for q in qs])
+            cases[name] = dict(d=d, loss=loss, tau_out=tau_out, act=act, load_prior=load_prior,
+                               prior_var=cfg.prior_var, q=qs, logp=np.array(lps, np.float64),
+                               grad=np.stack(grads).astype(np.float32))
+    cfg.act, cfg.load_prior, cfg.loss, cfg.tau_out = "tanh", False, "NLL", 0.0025
+    flat = {}
+    for name, c in cases.items():
+        for k, v in c.items():
+            flat[f"{name}/{k}"] = np.asarray(v)
+    out = os.path.join(GOLDEN, "bnn_vi_hmc_logp_grad.npz")
+    np.savez_compressed(out, **flat)
+    print("wrote", out, {k: float(v["logp"][0]) for k, v in cases.items()})
+
+
+def _don_module_cfg(m, arch: DeepONetArch, load_prior=False):
+    cfg = m.cfg
+    cfg.branch_depth, cfg.trunk_depth, cfg.activation = arch.depth_branch, arch.depth_trunk, arch.act
+    cfg.sample_data, cfg.load_prior = False, load_prior
+    return cfg
+
+
+def deeponet_cases():
+    """Reference closures Operator_network/VI_HMC/main_VI_HMC_burgers.py:27-180 (VI split) and
+    Operator_network/HMC/main_HMC_splitting.py:79-258 (full HMC, M=2 split) on synthetic Burgers-shaped data."""
+    flat = {}
+    m = ref_loader.load_deeponet_vi_hmc()
+    ms = ref_loader.load_deeponet_split_hmc()
+    for name, arch, n_train, n_t, n_x, frac in [
+        ("small", DeepONetArch(width_branch=16, width_trunk=16, in_branch=12, depth_branch=3, depth_trunk=4,
+                               output_neurons=8), 6, 5, 7, 0.25),
+        ("full", DeepONetArch(), 8, 3, 11, 0.10),
+    ]:
+        x1, x2, y, theta = synth.burgers_like(arch, n_train=n_train, n_t=n_t, n_x=n_x, seed=0)
+        mu, sigma, ind = synth.deeponet_vi_artifacts(theta, frac=frac, seed=1)
+        tr_data = (x1.unsqueeze(1), x2.unsqueeze(0), y)
+        # ---- VI-HMC closure (reduced vector) ----
+        with tempfile.TemporaryDirectory() as tmp:
+            cfg = _don_module_cfg(m, arch)
+            cfg.prior_file, cfg.prior_uid = tmp, "synthetic"
+            _write_artifacts(tmp, "synthetic", mu, sigma, ind)
+            net = m.DeepONet(arch.width_branch, arch.width_trunk, arch.in_branch, arch.in_trunk, arch.depth_branch,
+                             arch.depth_trunk, arch.act, arch.output_neurons)
+            assert sum(p.nelement() for p in net.parameters()) == arch.num_params
+            closure = m.define_model_log_prob(net, "NLL", tr_data, [torch.tensor(cfg.prior_var)], 1.0, device="cpu")
+            rs = np.random.RandomState(7)
+            d = len(ind)
+            qs = (mu.numpy()[ind][None] + sigma.numpy()[ind][None] * rs.randn(3, d)).astype(np.float32)
+            lps, grads = zip(*[_grad(closure, torch.from_numpy(q)) for q in qs])
+            flat[f"{name}/vi/q"] = qs
+            flat[f"{name}/vi/logp"] = np.array(lps, np.float64)
+            flat[f"{name}/vi/grad"] = np.stack(grads).astype(np.float32)
+            flat[f"{name}/vi/prior_var"] = np.asarray(cfg.prior_var)
+        # ---- full-HMC closure + M=2 split closures ----
+        cfgs = ms.cfg
+        cfgs.branch_depth, cfgs.trunk_depth, cfgs.activation = arch.depth_branch, arch.depth_trunk, arch.act
+        cfgs.sample_data, cfgs.load_prior, cfgs.dataset = False, False, "Burgers"
+        net = ms.DeepONet(arch.width_branch, arch.width_trunk, arch.in_branch, arch.in_trunk, arch.depth_branch,
+                          arch.depth_trunk, arch.act, arch.output_neurons)
+        tau_list = [torch.tensor(cfgs.prior_var)]
+        full = ms.define_model_log_prob(net, "NLL", tr_data, tau_list, 1.0, device="cpu")
+        half = n_train // 2
+        split_data = [(tr_data[0][i * half:(i + 1) * half], tr_data[1], tr_data[2][i * half:(i + 1) * half]) for i in range(2)]
+        splits = ms.define_split_model_log_prob(net, "NLL", split_data, 2, tau_list, 1.0, device="cpu", verbose=False)
+        rs = np.random.RandomState(8)
+        qs = (theta.numpy()[None] + 0.01 * rs.randn(2, arch.num_params)).astype(np.float32)
+        lps, grads = zip(*[_grad(full, torch.from_numpy(q)) for q in qs])
+        flat[f"{name}/full/q"] = qs
+        flat[f"{name}/full/logp"] = np.array(lps, np.float64)
+        flat[f"{name}/full/grad"] = np.stack(grads).astype(np.float32)
+        for si, sc in enumerate(splits):
+            lps, grads = zip(*[_grad(sc, torch.from_numpy(q)) for q in qs])
+            flat[f"{name}/split{si}/logp"] = np.array(lps, np.float64)
+            flat[f"{name}/split{si}/grad"] = np.stack(grads).astype(np.float32)
+        flat[f"{name}/meta"] = np.array([n_train, n_t, n_x, int(round(frac * 1000))], np.int64)
+        print(name, "D", arch.num_params, "d", len(ind), "logp", flat[f"{name}/vi/logp"], flat[f"{name}/full/logp"])
+    out = os.path.join(GOLDEN, "deeponet_logp_grad.npz")
+    np.savez_compressed(out, **flat)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    bnn_data_file()
+    bnn_vi_hmc_cases()
+    deeponet_cases()

@@ -1,0 +1,97 @@
+"""CPU: pin the oracle restatement (oracle/closures.py) against golden vectors produced by the
+REAL reference closures (oracle/make_golden.py).  Tolerances: the restatement uses the same torch ops
+in the same order, so fp32 agreement is to a few ulp of the ~1e5-sized log-probability."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import closures as oc
+
+
+@pytest.mark.parametrize("name", cases.BNN_CASES)
+def test_bnn_closure_matches_reference_golden(name):
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, name)
+    closure = cases.bnn_oracle(case)
+    for q, lp_ref, g_ref in zip(case["q"], case["logp"], case["grad"]):
+        lp, grad = oc.value_and_grad(closure, torch.from_numpy(q))
+        assert abs(float(lp) - lp_ref) <= 1e-6 * abs(lp_ref)
+        np.testing.assert_allclose(grad.numpy(), g_ref, rtol=1e-5, atol=1e-5 * np.abs(g_ref).max())
+
+
+@pytest.mark.parametrize("name", cases.BNN_CASES)
+def test_bnn_fp64_twin_brackets_fp32(name):
+    """The fp64 twin attributes error: fp32 reference and fp64 oracle agree to fp32 rounding of a 1e5-sized sum."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, name)
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    for q, lp_ref, g_ref in zip(case["q"], case["logp"], case["grad"]):
+        lp, grad = oc.value_and_grad(closure, torch.from_numpy(q).double())
+        assert abs(float(lp) - lp_ref) <= 2e-6 * abs(lp_ref)
+        np.testing.assert_allclose(grad.numpy(), g_ref, rtol=2e-4, atol=2e-5 * np.abs(g_ref).max())
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_deeponet_closures_match_reference_golden(name):
+    g = cases.load_golden("deeponet_logp_grad.npz")
+    inp = cases.don_inputs(name)
+    vi = cases.don_oracle(inp, "vi")
+    for q, lp_ref, g_ref in zip(g[f"{name}/vi/q"], g[f"{name}/vi/logp"], g[f"{name}/vi/grad"]):
+        lp, grad = oc.value_and_grad(vi, torch.from_numpy(q))
+        assert abs(float(lp) - lp_ref) <= 1e-6 * abs(lp_ref)
+        np.testing.assert_allclose(grad.numpy(), g_ref, rtol=1e-5, atol=1e-5 * np.abs(g_ref).max())
+    full = cases.don_oracle(inp, "full")
+    splits = cases.don_oracle(inp, "split")
+    for i, q in enumerate(g[f"{name}/full/q"]):
+        lp, grad = oc.value_and_grad(full, torch.from_numpy(q))
+        lp_ref, g_ref = g[f"{name}/full/logp"][i], g[f"{name}/full/grad"][i]
+        assert abs(float(lp) - lp_ref) <= 1e-6 * abs(lp_ref)
+        np.testing.assert_allclose(grad.numpy(), g_ref, rtol=1e-5, atol=1e-5 * np.abs(g_ref).max())
+        for si, sc in enumerate(splits):
+            lp, grad = oc.value_and_grad(sc, torch.from_numpy(q))
+            lp_ref, g_ref = g[f"{name}/split{si}/logp"][i], g[f"{name}/split{si}/grad"][i]
+            assert abs(float(lp) - lp_ref) <= 1e-6 * abs(lp_ref)
+            np.testing.assert_allclose(grad.numpy(), g_ref, rtol=1e-5, atol=1e-5 * np.abs(g_ref).max())
+
+
+def test_split_closures_sum_to_full():
+    """Size-independent property: sum of the M split log-posteriors == the full log-posterior."""
+    inp = cases.don_inputs("small")
+    full = cases.don_oracle(inp, "full", dtype=torch.float64)
+    splits = cases.don_oracle(inp, "split", dtype=torch.float64)
+    q = inp["theta"].double()
+    lp, grad = oc.value_and_grad(full, q)
+    parts = [oc.value_and_grad(s, q) for s in splits]
+    assert abs(float(lp) - sum(float(p[0]) for p in parts)) < 1e-8 * abs(float(lp))
+    np.testing.assert_allclose(sum(p[1] for p in parts).numpy(), grad.numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_reference_still_agrees_when_present():
+    """When /root/reference is mounted (build container), re-run one real reference closure live."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not mounted (GPU box)")
+    import os
+    import tempfile
+
+    m = ref_loader.load_bnn_vi_hmc()
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    with tempfile.TemporaryDirectory() as tmp:
+        torch.save(case["mu"], os.path.join(tmp, "means_flattened_t"))
+        torch.save(case["sigma"], os.path.join(tmp, "stds_flattened_t"))
+        np.save(os.path.join(tmp, "gradient_indices_t.npy"), case["ind"])
+        m.cfg.prior_file, m.cfg.prior_uid = tmp, "t"
+        net = m.get_model(True)
+        x, y, _, _ = ref_loader.load_bnn_data()
+        numels = [w.nelement() for w in net.parameters()]
+        shapes = [w.shape for w in net.parameters()]
+        closure = m.define_model_log_prob(net, "NLL", x, y, numels, shapes,
+                                          [torch.tensor(1.0)] * 6, 0.0025, device="cpu", dt_string="t")
+        q = torch.from_numpy(case["q"][0]).requires_grad_()
+        lp = closure(q)
+        (gr,) = torch.autograd.grad(lp, q)
+    assert abs(float(lp) - case["logp"][0]) <= 1e-6 * abs(case["logp"][0])
+    np.testing.assert_allclose(gr.numpy(), case["grad"][0], rtol=1e-6, atol=1e-3)
