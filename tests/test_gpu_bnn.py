@@ -1,0 +1,255 @@
+"""GPU parity tests for the BNN (small-MLP) path, all through the C ABI (libvihmc.so via ctypes).
+
+Tolerances (stated per BASELINE.json north_star): log-posterior and gradient within rtol 1e-5 in fp32;
+the gradient tolerance is taken relative to the largest component of the reference gradient because
+individual components pass through zero.  Integer work (Philox, uniform bits) is bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import closures as oc
+from oracle import hamiltorch_restated as hr
+from oracle import philox_ref
+from vihmc import engine, samplers
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _assert_grad_close(got, ref, rtol=RTOL):
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * scale)
+
+
+@pytest.mark.parametrize("name", cases.BNN_CASES)
+def test_logp_grad_matches_reference_golden(name):
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, name)
+    spec = cases.bnn_spec(case)
+    logp, grad = engine.logp_grad(spec, torch.from_numpy(case["q"]))
+    np.testing.assert_allclose(logp.cpu().numpy(), case["logp"], rtol=RTOL)
+    for i in range(len(case["q"])):
+        _assert_grad_close(grad[i].cpu().numpy(), case["grad"][i])
+
+
+def test_logp_grad_many_chains_vs_fp64_oracle():
+    """C = 300 chains (ragged vs the warp/CTA geometry) against the fp64 twin of the oracle."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    rs = np.random.RandomState(3)
+    mu, sg = case["mu"].numpy()[case["ind"]], case["sigma"].numpy()[case["ind"]]
+    q = (mu[None] + 3 * sg[None] * rs.randn(300, case["d"])).astype(np.float32)
+    logp, grad = engine.logp_grad(spec, torch.from_numpy(q))
+    logp, grad = logp.cpu().numpy(), grad.cpu().numpy()
+    for c in range(0, 300, 7):
+        lp, gr = oc.value_and_grad(closure, torch.from_numpy(q[c]).double())
+        assert abs(logp[c] - float(lp)) <= RTOL * abs(float(lp))
+        _assert_grad_close(grad[c], gr.numpy())
+
+
+def test_full_hmc_hamiltorch_form_vs_oracle():
+    """cfg1: d = D = 141, prior N(0, tau^-1/2) per tensor with tau = 1, 'regression' likelihood, tau_out = 400."""
+    from vihmc import synth
+
+    x, y, _, _ = synth.bnn_data()
+    arch = synth.bnn_arch()
+    numels = arch.tensor_numels()
+    spec = samplers.define_model_log_prob_hamiltorch(arch, "regression", x, y, numels, None, [1.0] * len(numels), 400.0)
+    closure = oc.BnnLogProb(x=x, y=y, widths=(10, 10), loss="regression", tau_out=400.0, prior=("tau", [1.0] * 6),
+                            dtype=torch.float64)
+    q = synth.default_linear_init(arch, seed=0).unsqueeze(0).repeat(4, 1)
+    q[1:] += 0.1 * torch.from_numpy(np.random.RandomState(0).randn(3, 141).astype(np.float32))
+    logp, grad = engine.logp_grad(spec, q)
+    for c in range(4):
+        lp, gr = oc.value_and_grad(closure, q[c].double())
+        assert abs(float(logp[c]) - float(lp)) <= RTOL * abs(float(lp))
+        _assert_grad_close(grad[c].cpu().numpy(), gr.numpy())
+
+
+def test_philox_uniforms_bit_exact_and_normals_close():
+    seed, chain0, C, d = 0x1234_5678_9ABC_DEF0, 5, 37, 141
+    for it in (0, 1, 99):
+        u = engine.uniform_philox(seed, it, chain0, C).cpu().numpy()
+        ref = philox_ref.uniforms(seed, chain0, C, it)
+        assert np.array_equal(u.view(np.uint32), ref.view(np.uint32))
+        z = engine.momentum_philox(seed, it, chain0, C, d).cpu().numpy()
+        zr = philox_ref.normals(seed, chain0, C, it, d)
+        np.testing.assert_allclose(z, zr, rtol=2e-6, atol=2e-6)
+    # moments of a large draw
+    z = engine.momentum_philox(7, 0, 0, 4096, 256).cpu().numpy().ravel()
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+
+
+def _run_oracle_chain(closure, q0, S, L, eps, burn, momenta, uniforms, **kw):
+    trace = {}
+    out = hr.sample(closure, q0, num_samples=S, num_steps_per_sample=L, step_size=eps, burn=burn, momenta=momenta,
+                    uniforms=uniforms, trace=trace, **kw)
+    return torch.stack(out), trace
+
+
+def test_single_trajectory_matches_oracle():
+    """One leapfrog trajectory with injected momentum: end point, H0 and H1 against the fp32 and fp64 oracle."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    d, L, eps = case["d"], 25, 5e-4
+    rs = np.random.RandomState(11)
+    q0 = torch.from_numpy(case["q"][0])
+    p = torch.from_numpy(rs.randn(2, 1, d).astype(np.float32))
+    u = torch.full((2, 1), 1e-30)  # log u = -69: both proposals accepted, so row 1 is the trajectory end point
+    res = engine.run_sampler([spec], q0[None], 2, L, eps, burn=0, inject_momenta=p, inject_uniforms=u)
+    for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 2e-5)):
+        closure = cases.bnn_oracle(case, dtype=dtype)
+        out, tr = _run_oracle_chain(closure, q0.to(dtype), 2, L, eps, 0, p[:, 0].to(dtype), u[:, 0])
+        np.testing.assert_allclose(res.samples[1, 0].numpy(), out[1].numpy(), rtol=tol, atol=tol * float(out[1].abs().max()))
+        np.testing.assert_allclose(res.hamiltonians[:, 0, 0].numpy(), tr["H0"], rtol=RTOL)
+        np.testing.assert_allclose(res.hamiltonians[:, 0, 1].numpy(), tr["H1"], rtol=RTOL)
+
+
+def test_accept_reject_identical_over_short_run():
+    """8 chains x 40 iterations with injected momenta/uniforms: decisions identical to the fp64 oracle wherever
+    |rho - log u| exceeds the fp32 resolution of H (~1e5 magnitude => ulp 0.008; margin 0.25)."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    d, S, L, eps, Cn, burn = case["d"], 40, 12, 2e-4, 8, 5
+    rs = np.random.RandomState(5)
+    mu, sg = case["mu"].numpy()[case["ind"]], case["sigma"].numpy()[case["ind"]]
+    q0 = torch.from_numpy((mu[None] + sg[None] * rs.randn(Cn, d)).astype(np.float32))
+    p = torch.from_numpy(rs.randn(S, Cn, d).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(0.01, 1.0, size=(S, Cn)).astype(np.float32))
+    res = engine.run_sampler([spec], q0, S, L, eps, burn=burn, inject_momenta=p, inject_uniforms=u)
+    assert res.samples.shape == (S - burn, Cn, d)
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    checked = agree = 0
+    for c in range(Cn):
+        out, tr = _run_oracle_chain(closure, q0[c].double(), S, L, eps, burn, p[:, c].double(), u[:, c])
+        acc_ref = np.array(tr["accept"])
+        rho = np.minimum(0.0, np.array(tr["H0"]) - np.array(tr["H1"]))
+        margin = np.abs(rho - np.log(u[:, c].numpy().astype(np.float64)))
+        acc = res.accepted[:, c].numpy().astype(bool)
+        # once a decision differs the chains diverge, so compare up to the first low-margin iteration
+        first_low = int(np.argmax(margin < 0.25)) if (margin < 0.25).any() else S
+        checked += first_low
+        agree += int((acc[:first_low] == acc_ref[:first_low]).sum())
+        assert np.array_equal(acc[:first_low], acc_ref[:first_low])
+        if first_low == S:
+            np.testing.assert_allclose(res.samples[:, c].numpy(), out.numpy(), rtol=2e-4, atol=2e-4)
+    assert checked >= S  # the filter must leave something to compare
+    assert agree == checked
+
+
+def test_storage_rule_and_fallback():
+    """hamiltorch bookkeeping: rows = num_samples - burn, row 0 = params_init, rejected iterations repeat the last
+    stored row, and the first post-burn rejection falls back to params_init."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    d, S, L, eps, burn = case["d"], 8, 5, 5e-4, 2
+    q0 = torch.from_numpy(case["q"][0])[None]
+    p = torch.from_numpy(np.random.RandomState(2).randn(S, 1, d).astype(np.float32))
+    u = torch.full((S, 1), 1e-30)
+    u[3, 0] = 1.0 - 1e-7   # n = 3 = burn + 1: log u ~ 0 > rho  => reject
+    u[5, 0] = 1.0 - 1e-7
+    res = engine.run_sampler([spec], q0, S, L, eps, burn=burn, inject_momenta=p, inject_uniforms=u)
+    acc = res.accepted[:, 0].numpy()
+    assert acc.tolist() == [1, 1, 1, 0, 1, 0, 1, 1]
+    rows = res.samples[:, 0]
+    assert rows.shape[0] == S - burn
+    assert torch.equal(rows[0], q0[0])
+    assert torch.equal(rows[1], q0[0])          # n=3 rejected -> falls back to the last STORED row = params_init
+    assert not torch.equal(rows[2], rows[1])    # n=4 accepted
+    assert torch.equal(rows[3], rows[2])        # n=5 rejected -> repeats
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    out, tr = _run_oracle_chain(closure, q0[0].double(), S, L, eps, burn, p[:, 0].double(), u[:, 0])
+    assert tr["accept"] == [bool(a) for a in acc]
+    np.testing.assert_allclose(rows.numpy(), out.numpy(), rtol=1e-4, atol=1e-4)
+    # logp of every stored row is the log-posterior of that row
+    lp, _ = engine.logp_grad(spec, rows, need_grad=False)
+    np.testing.assert_allclose(res.logp[:, 0].numpy(), lp.cpu().numpy(), rtol=1e-6)
+
+
+def test_sharding_invariance_bit_exact():
+    """Philox is keyed on the GLOBAL chain id: 16 chains in one call == two calls of 8 with chain_offset."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    rs = np.random.RandomState(9)
+    mu, sg = case["mu"].numpy()[case["ind"]], case["sigma"].numpy()[case["ind"]]
+    q0 = torch.from_numpy((mu[None] + sg[None] * rs.randn(16, case["d"])).astype(np.float32))
+    kw = dict(num_samples=6, num_steps=7, step_size=5e-4, burn=1, seed=42)
+    whole = engine.run_sampler([spec], q0, **kw)
+    lo = engine.run_sampler([spec], q0[:8], chain_offset=0, **kw)
+    hi = engine.run_sampler([spec], q0[8:], chain_offset=8, **kw)
+    assert torch.equal(whole.samples[:, :8], lo.samples) and torch.equal(whole.samples[:, 8:], hi.samples)
+    assert torch.equal(whole.accepted[:, 8:], hi.accepted)
+    # different seeds give different draws
+    other = engine.run_sampler([spec], q0, **{**kw, "seed": 43})
+    assert not torch.equal(other.samples, whole.samples)
+
+
+def test_persistent_kernel_matches_general_sampler():
+    """The fused one-launch sampler and the host-orchestrated building-block sampler implement the same chain."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    for name in ("d40_nll", "d141_nll"):
+        case = cases.bnn_case(g, name)
+        spec = cases.bnn_spec(case)
+        q0 = torch.from_numpy(case["q"][:4])
+        kw = dict(num_samples=5, num_steps=9, step_size=3e-4, burn=1, seed=3)
+        a = engine.run_sampler([spec], q0, **kw)
+        b = engine.run_sampler([spec], q0, force_general=True, **kw)
+        assert torch.equal(a.accepted, b.accepted)
+        np.testing.assert_allclose(a.samples.numpy(), b.samples.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(a.hamiltonians.numpy(), b.hamiltonians.numpy(), rtol=1e-6)
+
+
+def test_dual_averaging_matches_oracle():
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    d, S, L, burn = case["d"], 12, 6, 8
+    rs = np.random.RandomState(21)
+    q0 = torch.from_numpy(case["q"][0])[None]
+    p = torch.from_numpy(rs.randn(S, 1, d).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(0.05, 1, size=(S, 1)).astype(np.float32))
+    res = engine.run_sampler([spec], q0, S, L, 1e-4, burn=burn, adapt_step_size=True, inject_momenta=p, inject_uniforms=u)
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    _, tr = _run_oracle_chain(closure, q0[0].double(), S, L, 1e-4, burn, p[:, 0].double(), u[:, 0], sampler=hr.Sampler.HMC_NUTS)
+    if tr["accept"] == [bool(a) for a in res.accepted[:, 0].numpy()]:
+        assert abs(float(res.step_sizes[0]) - tr["final_step_size"]) <= 2e-3 * tr["final_step_size"]
+    # with or without identical decisions the first adapted step sizes follow the same recursion
+    assert float(res.step_sizes[0]) > 0
+
+
+def test_predict_matches_oracle_forward():
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    from vihmc import synth
+
+    _, _, x_val, y_val = synth.bnn_data()
+    q = torch.from_numpy(case["q"])
+    pred, logps = samplers.predict_model(spec, q, x=x_val, y=y_val)
+    assert pred.shape == (len(q), 300, 1)
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    for i in range(len(q)):
+        ref = closure.forward(q[i].double(), x=x_val)
+        np.testing.assert_allclose(pred[i].numpy(), ref.detach().numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_reference_style_call_returns_list():
+    """samplers.sample with a 1-D params_init returns hamiltorch's list of (num_samples - burn) 1-D tensors."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    out = samplers.sample(spec, torch.from_numpy(case["q"][0]), num_samples=6, num_steps_per_sample=4, step_size=5e-4)
+    assert isinstance(out, list) and len(out) == 6 and out[0].shape == (case["d"],)
+    assert np.asarray([o.numpy() for o in out]).shape == (6, case["d"])
+    many = samplers.sample(spec, torch.from_numpy(case["q"][0]), num_samples=6, num_steps_per_sample=4, step_size=5e-4,
+                           num_chains=5, burn=2)
+    assert many.shape == (4, 5, case["d"])

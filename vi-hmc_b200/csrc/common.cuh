@@ -1,0 +1,149 @@
+// Shared device/host helpers for libvihmc (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vihmc.h"
+
+namespace vihmc {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (thread-local message behind vihmc_last_error)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define VIHMC_CUDA_OK(expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t err__ = (expr);                                                                     \
+    if (err__ != cudaSuccess)                                                                       \
+      return ::vihmc::fail(VIHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                           __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define VIHMC_LAUNCH_OK(what)                                                                       \
+  do {                                                                                              \
+    cudaError_t err__ = cudaGetLastError();                                                         \
+    if (err__ != cudaSuccess)                                                                       \
+      return ::vihmc::fail(VIHMC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(err__)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  counter = (c0,c1,c2,c3), key = (k0,k1).
+// Engine convention: key = 64-bit seed; counter = (global chain id, iteration, block, stream).
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { STREAM_MOMENTUM = 0, STREAM_UNIFORM = 1, STREAM_VI_REDRAW = 2, STREAM_INIT = 3 };
+
+struct u32x4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c0), hi1 = __umulhi(M1, c2);
+#else
+    uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c0) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c2) >> 32);
+#endif
+    uint32_t lo0 = M0 * c0, lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
+// 24-bit uniform strictly inside (0,1): exactly representable in fp32, log() always finite.
+__host__ __device__ __forceinline__ float u32_to_unit(uint32_t v) {
+  return ((float)(v >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+// Box-Muller on two 32-bit words -> two N(0,1).  Accurate (non-fast-math) logf/sincospif.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  float u1 = u32_to_unit(a), u2 = u32_to_unit(b);
+  float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// four normals for coordinates 4*block .. 4*block+3 of (chain, iteration, stream)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t chain, uint32_t iteration, uint32_t block,
+                                                 uint32_t stream) {
+  // 64-bit chain ids are folded: low word in c0, high word xored into the stream word's upper bits.
+  u32x4 r = philox4x32_10((uint32_t)chain, iteration, block, stream ^ ((uint32_t)(chain >> 32) << 8),
+                          (uint32_t)seed, (uint32_t)(seed >> 32));
+  float4 z;
+  box_muller(r.x, r.y, z.x, z.y);
+  box_muller(r.z, r.w, z.z, z.w);
+  return z;
+}
+
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t chain, uint32_t iteration) {
+  u32x4 r = philox4x32_10((uint32_t)chain, iteration, 0u, STREAM_UNIFORM ^ ((uint32_t)(chain >> 32) << 8),
+                          (uint32_t)seed, (uint32_t)(seed >> 32));
+  return u32_to_unit(r.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions: fixed butterfly order => bit-reproducible, identical on every lane
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// activations (my_make_func.py:36-43): value and derivative w.r.t. pre-activation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(int act, float z, float& dact) {
+  if (act == VIHMC_ACT_TANH) {
+    float h = tanhf(z);
+    dact = 1.0f - h * h;
+    return h;
+  } else if (act == VIHMC_ACT_RELU) {
+    dact = z > 0.0f ? 1.0f : 0.0f;
+    return z > 0.0f ? z : 0.0f;
+  } else {
+    float s, c;
+    sincosf(z, &s, &c);
+    dact = c;
+    return s;
+  }
+}
+
+// Gaussian likelihood pieces (main_VI_HMC.py:132-136; GaussianNLLLoss clamps var at 1e-6, full=False)
+struct Likelihood {
+  float ll_const;   // per-output additive constant: NLL: -0.5 log v ; regression: 0
+  float half_prec;  // NLL: 0.5 / v ; regression: 0.5 tau
+  float prec;       // NLL: 1 / v   ; regression: tau          (d loglik / d o = -prec (o - y))
+};
+
+__host__ __device__ __forceinline__ Likelihood make_likelihood(int loss, float tau_out) {
+  Likelihood l;
+  if (loss == VIHMC_LOSS_NLL) {
+    float v = tau_out < 1e-6f ? 1e-6f : tau_out;
+    l.ll_const = -0.5f * logf(v);
+    l.half_prec = 0.5f / v;
+    l.prec = 1.0f / v;
+  } else {
+    l.ll_const = 0.0f;
+    l.half_prec = 0.5f * tau_out;
+    l.prec = tau_out;
+  }
+  return l;
+}
+
+// hamiltorch writes `p += c * g` as two separately rounded torch ops (mul kernel, add kernel):
+// mirror that rounding instead of letting nvcc contract to an FMA.
+__device__ __forceinline__ float axpy_unfused(float a, float x, float y) { return __fadd_rn(y, __fmul_rn(a, x)); }
+
+}  // namespace vihmc

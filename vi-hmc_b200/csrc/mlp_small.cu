@@ -1,0 +1,120 @@
+// Small-MLP path: host-side validation, kernel selection and launch geometry (kernels: mlp_small.cuh).
+#include "mlp_small.cuh"
+
+namespace vihmc {
+
+// ------------------------------------------------------------------------------------------------
+// host side: validation, dispatch on (padded width, hidden layers), launch geometry
+// ------------------------------------------------------------------------------------------------
+static int pick_width(int maxw) {
+  if (maxw <= 10) return 10;
+  if (maxw <= 16) return 16;
+  if (maxw <= 32) return 32;
+  return 0;
+}
+
+bool mlp_small_supported(const vihmc_problem* p) {
+  if (p->model_kind != VIHMC_MODEL_MLP) return false;
+  const int nh = p->n_layers_a - 1;
+  if (nh < 1 || nh > kMaxHidden) return false;
+  if (p->dims_a[nh] != 1) return false;
+  int maxw = 0;
+  for (int l = 0; l < nh; ++l) maxw = p->dims_a[l] > maxw ? p->dims_a[l] : maxw;
+  if (pick_width(maxw) == 0) return false;
+  if (p->in_a < 1 || p->in_a > 64) return false;
+  const SmallLayout L = make_layout(pick_width(maxw), nh, p->in_a, p->d, p->N);
+  if (L.total - L.act_base >= 65536) return false;          // phase-B offsets are packed in 16 bits
+  return (size_t)L.total * sizeof(float) <= 200u * 1024u;  // one chain must fit in one CTA's smem
+}
+
+static int fill_params(const vihmc_problem* p, SmallParams& P, int& W) {
+  if (!mlp_small_supported(p))
+    return fail(VIHMC_ERR_UNSUPPORTED, "MLP outside the small-net kernel's range (<=4 hidden layers of width <=32, out_dim 1)");
+  if (p->x == nullptr || p->y == nullptr) return fail(VIHMC_ERR_INVALID, "x and y must be device pointers");
+  if ((p->frozen == nullptr) != (p->sens_ind == nullptr))
+    return fail(VIHMC_ERR_INVALID, "frozen and sens_ind must be given together");
+  if (p->sens_ind == nullptr && p->d != p->D) return fail(VIHMC_ERR_INVALID, "d != D requires sens_ind");
+  if (p->d < 1 || p->d > p->D || p->N < 1) return fail(VIHMC_ERR_INVALID, "bad d/D/N");
+  const int nh = p->n_layers_a - 1;
+  long long D = 0;
+  int prev = p->in_a, maxw = 0;
+  for (int l = 0; l <= nh; ++l) {
+    const int o = p->dims_a[l];
+    if (o < 1) return fail(VIHMC_ERR_INVALID, "layer width must be positive");
+    D += (long long)o * prev + ((l < nh || p->last_bias) ? o : 0);
+    if (l < nh && o > maxw) maxw = o;
+    prev = o;
+  }
+  if (D != p->D) return fail(VIHMC_ERR_INVALID, "D=%lld does not match the architecture (%lld)", (long long)p->D, D);
+  if (p->prior_scale == 0.0f) return fail(VIHMC_ERR_INVALID, "prior_scale must be non-zero");
+  W = pick_width(maxw);
+  P.act = p->act; P.loss = p->loss; P.last_bias = p->last_bias; P.n_hidden = nh; P.in_dim = p->in_a;
+  for (int l = 0; l < kMaxHidden; ++l) P.widths[l] = l < nh ? p->dims_a[l] : 0;
+  P.D = p->D; P.d = p->d; P.N = p->N;
+  P.tau_out = p->tau_out; P.inv_prior_scale = 1.0f / p->prior_scale;
+  P.prior_sigma_scalar = p->prior_sigma_scalar; P.prior_log_norm = p->prior_log_norm;
+  P.x = p->x; P.y = p->y; P.frozen = p->frozen; P.prior_mu = p->prior_mu; P.prior_sigma = p->prior_sigma;
+  P.sens_ind = reinterpret_cast<const long long*>(p->sens_ind);
+  P.lay = make_layout(W, nh, p->in_a, p->d, p->N);
+  return VIHMC_OK;
+}
+
+int mlp_small_launch_w10(SmallOp, const SmallParams&, const SmallLaunch&, cudaStream_t);
+int mlp_small_launch_w16(SmallOp, const SmallParams&, const SmallLaunch&, cudaStream_t);
+int mlp_small_launch_w32(SmallOp, const SmallParams&, const SmallLaunch&, cudaStream_t);
+
+// One warp per chain.  Few chains: 1 warp per CTA so the 148 SMs fill evenly; many chains: up to 4
+// warps per CTA so the 32-CTA/SM limit does not cap residency.
+static void pick_geometry(const SmallLayout& L, long long C, SmallLaunch& a) {
+  const size_t per_chain = (size_t)L.total * sizeof(float);
+  int wpb = 1;
+  while (wpb < 4 && C > (long long)148 * 24 * wpb && per_chain * (wpb * 2) <= 200u * 1024u) wpb *= 2;
+  a.warps_per_block = wpb;
+  a.blocks = (int)((C + wpb - 1) / wpb);
+  a.smem = per_chain * wpb;
+  a.C = C;
+}
+
+static int dispatch(int W, SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
+  if (W == 10) return mlp_small_launch_w10(op, P, a, st);
+  if (W == 16) return mlp_small_launch_w16(op, P, a, st);
+  if (W == 32) return mlp_small_launch_w32(op, P, a, st);
+  return fail(VIHMC_ERR_UNSUPPORTED, "no small-MLP instantiation for width %d", W);
+}
+
+int mlp_small_logp_grad(const vihmc_problem* prob, long long C, const float* q, float* logp, float* grad, cudaStream_t st) {
+  SmallParams P{};
+  int W = 0;
+  if (int rc = fill_params(prob, P, W)) return rc;
+  SmallLaunch a{};
+  pick_geometry(P.lay, C, a);
+  a.q = q; a.logp = logp; a.grad = grad;
+  return dispatch(W, kOpLogpGrad, P, a, st);
+}
+
+int mlp_small_predict(const vihmc_problem* prob, long long C, const float* q, float* out, cudaStream_t st) {
+  SmallParams P{};
+  int W = 0;
+  if (int rc = fill_params(prob, P, W)) return rc;
+  SmallLaunch a{};
+  pick_geometry(P.lay, C, a);
+  a.q = q; a.out = out;
+  return dispatch(W, kOpPredict, P, a, st);
+}
+
+int mlp_small_sample(const vihmc_problem* prob, const vihmc_sampler_cfg* cfg, long long C, const float* q0, float* samples,
+                     const vihmc_sampler_io* io, cudaStream_t st) {
+  SmallParams P{};
+  int W = 0;
+  if (int rc = fill_params(prob, P, W)) return rc;
+  SmallLaunch a{};
+  pick_geometry(P.lay, C, a);
+  a.A.cfg = *cfg; a.A.C = C; a.A.q0 = q0; a.A.samples = samples;
+  if (io != nullptr) {
+    a.A.accepted = io->accepted; a.A.hamiltonians = io->hamiltonians; a.A.logp_out = io->logp; a.A.step_sizes = io->step_sizes;
+    a.A.inj_p = io->inject_momenta; a.A.inj_u = io->inject_uniforms;
+  }
+  return dispatch(W, kOpSample, P, a, st);
+}
+
+}  // namespace vihmc

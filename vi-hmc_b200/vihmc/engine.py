@@ -1,0 +1,300 @@
+"""Device plumbing between LogProbSpec (host description) and the C ABI (libvihmc.so).
+
+torch is used for device memory, streams and host<->device copies only; all arithmetic happens in
+the CUDA library.  Every entry point raises if CUDA or the library is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spec import (LogProbSpec, MLPArch, DeepONetArch, MODEL_DEEPONET, MODEL_MLP, act_code, loss_code)
+
+INTEGRATOR_LEAPFROG, INTEGRATOR_SPLITTING = 0, 1
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.VihmcError(-2, "no CUDA device: the vihmc engine has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.VihmcError(-2, f"device {dev} is not a CUDA device: the vihmc engine has no CPU fallback")
+    return dev
+
+
+def _to_dev(t, dev, dtype=torch.float32) -> Optional[torch.Tensor]:
+    """Host tensors are staged through pinned memory so the H2D copy is a real async DMA."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    t = t.detach()
+    if t.device.type == "cuda":
+        return t.to(device=dev, dtype=dtype).contiguous()
+    t = t.to(dtype).contiguous()
+    try:
+        t = t.pin_memory()
+    except RuntimeError:
+        pass
+    return t.to(dev, non_blocking=True)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Prepared:
+    """A LogProbSpec resident on one GPU + its vihmc_problem struct (keeps the tensors alive)."""
+
+    def __init__(self, spec: LogProbSpec, device=None):
+        spec.validate()
+        self.spec = spec
+        self.device = _require_cuda(device)
+        dev = self.device
+        arch = spec.arch
+        p = _lib.Problem()
+        p.model_kind = spec.model_kind
+        p.act = act_code(arch.act)
+        p.loss = loss_code(spec.loss)
+        if isinstance(arch, MLPArch):
+            dims = [o for o, _ in arch.layer_dims]
+            if len(dims) > _lib.MAX_LAYERS:
+                raise ValueError("too many layers")
+            p.last_bias, p.impose_bc = int(arch.last_bias), 0
+            p.n_layers_a, p.n_layers_b, p.in_a, p.in_b = len(dims), 0, arch.in_dim, 0
+            for i, w in enumerate(dims):
+                p.dims_a[i] = w
+            x = spec.x.reshape(spec.N, arch.in_dim)
+            y = spec.y.reshape(spec.N, arch.out_dim)
+            p.P = 1
+        else:
+            da = [o for o, _ in arch.stack_dims("branch")]
+            db = [o for o, _ in arch.stack_dims("trunk")]
+            p.last_bias, p.impose_bc = 1, int(arch.impose_bc)
+            p.n_layers_a, p.n_layers_b, p.in_a, p.in_b = len(da), len(db), arch.in_branch, arch.in_trunk
+            for i, w in enumerate(da):
+                p.dims_a[i] = w
+            for i, w in enumerate(db):
+                p.dims_b[i] = w
+            x = spec.x.reshape(spec.N, arch.in_branch)
+            y = spec.y.reshape(spec.N, -1)
+            p.P = y.shape[1]
+        p.D, p.d, p.N = spec.D, spec.d, spec.N
+        p.tau_out, p.prior_scale, p.prior_sigma_scalar = float(spec.tau_out), float(spec.prior_scale), float(spec.prior_sigma_scalar)
+        sig_host = None if spec.prior_sigma is None else spec.prior_sigma.detach().cpu().to(torch.float32).contiguous()
+        lib = _lib.load()
+        p.prior_log_norm = lib.vihmc_prior_log_norm(None if sig_host is None else sig_host.data_ptr(), spec.d,
+                                                    float(spec.prior_sigma_scalar))
+        self.x = _to_dev(x, dev)
+        self.y = _to_dev(y, dev)
+        self.x2 = _to_dev(None if spec.x2 is None else spec.x2.reshape(-1, spec.x2.shape[-1]), dev)
+        self.frozen = _to_dev(spec.frozen, dev)
+        self.sens_ind = _to_dev(None if spec.sens_ind is None else np.asarray(spec.sens_ind, dtype=np.int64), dev, torch.int64)
+        self.prior_mu = _to_dev(spec.prior_mu, dev)
+        self.prior_sigma = _to_dev(spec.prior_sigma, dev)
+        p.x, p.x2, p.y = _ptr(self.x), _ptr(self.x2), _ptr(self.y)
+        p.frozen, p.sens_ind = _ptr(self.frozen), _ptr(self.sens_ind)
+        p.prior_mu, p.prior_sigma = _ptr(self.prior_mu), _ptr(self.prior_sigma)
+        self.problem = p
+        self._ws: Optional[torch.Tensor] = None
+
+    @property
+    def h2d_bytes(self) -> int:
+        ts = (self.x, self.y, self.x2, self.frozen, self.sens_ind, self.prior_mu, self.prior_sigma)
+        return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+    def workspace(self, chains: int) -> torch.Tensor:
+        need = int(_lib.load().vihmc_workspace_bytes(C.byref(self.problem), chains))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def prepare(spec: Union[LogProbSpec, Prepared], device=None) -> Prepared:
+    return spec if isinstance(spec, Prepared) else Prepared(spec, device)
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def logp_grad(spec, q: torch.Tensor, need_grad: bool = True):
+    """log-posterior [C] and gradient [C,d] for C parameter vectors q[C,d] (device tensors returned)."""
+    prep = prepare(spec)
+    dev = prep.device
+    q2 = _to_dev(q.reshape(-1, prep.spec.d), dev)
+    Cn = q2.shape[0]
+    logp = torch.empty(Cn, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(q2) if need_grad else None
+    ws = prep.workspace(Cn)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_logp_grad(C.byref(prep.problem), Cn, q2.data_ptr(), logp.data_ptr(), _ptr(grad),
+                                               ws.data_ptr(), ws.numel(), _stream(dev)))
+    return logp, grad
+
+
+def predict(spec, q: torch.Tensor) -> torch.Tensor:
+    """Model outputs for C parameter vectors: [C,N] (MLP) or [C,N,P] (DeepONet)."""
+    prep = prepare(spec)
+    dev = prep.device
+    q2 = _to_dev(q.reshape(-1, prep.spec.d), dev)
+    Cn = q2.shape[0]
+    shape = (Cn, prep.spec.N) if prep.spec.model_kind == MODEL_MLP else (Cn, prep.spec.N, int(prep.problem.P))
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    ws = prep.workspace(Cn)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_predict(C.byref(prep.problem), Cn, q2.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream(dev)))
+    return out
+
+
+@dataclass
+class SampleResult:
+    samples: torch.Tensor                  # [num_samples - burn, C, d]; row 0 is params_init
+    accepted: Optional[torch.Tensor]       # [num_samples, C] uint8
+    hamiltonians: Optional[torch.Tensor]   # [num_samples, C, 2]
+    logp: Optional[torch.Tensor]           # [num_samples - burn, C]
+    step_sizes: Optional[torch.Tensor]     # [C]
+    grad_evals_per_chain: int = 0
+    gpu_launches: int = 0
+
+    @property
+    def acceptance_rate(self) -> float:
+        return float(self.accepted.float().mean()) if self.accepted is not None else float("nan")
+
+
+def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: int, step_size: float, burn: int = 0,
+                integrator: int = INTEGRATOR_LEAPFROG, adapt_step_size: bool = False, desired_accept_rate: float = 0.8,
+                seed: int = 0, chain_offset: int = 0, hamiltorch_fallback_rule: bool = True, diagnostics: bool = True,
+                inject_momenta: Optional[torch.Tensor] = None, inject_uniforms: Optional[torch.Tensor] = None,
+                to_host: bool = True, force_general: bool = False) -> SampleResult:
+    """Advance C = q0.shape[0] chains.  specs: one LogProbSpec/Prepared (leapfrog) or several (splitting).
+
+    Inputs may be host tensors (they are copied to the GPU here); with ``to_host`` the result tensors are
+    copied back, so one call is a complete host-to-host sampling run.
+    """
+    preps = [prepare(s) for s in specs]
+    dev = preps[0].device
+    lib = _lib.load()
+    d = preps[0].spec.d
+    q0d = _to_dev(q0.reshape(-1, d), dev)
+    Cn = q0d.shape[0]
+    rows = num_samples - burn
+    if rows < 1:
+        raise RuntimeError("burn must be less than num_samples.")
+    cfg = _lib.SamplerCfg(num_samples=num_samples, num_steps=num_steps, burn=burn, integrator=integrator,
+                          adapt_step_size=int(adapt_step_size), hamiltorch_fallback_rule=int(hamiltorch_fallback_rule),
+                          step_size=step_size, desired_accept_rate=desired_accept_rate, seed=seed, chain_offset=chain_offset)
+    samples = torch.empty((rows, Cn, d), dtype=torch.float32, device=dev)
+    io = _lib.SamplerIO()
+    acc = ham = lp = eps = None
+    if diagnostics:
+        acc = torch.empty((num_samples, Cn), dtype=torch.uint8, device=dev)
+        ham = torch.empty((num_samples, Cn, 2), dtype=torch.float32, device=dev)
+        lp = torch.empty((rows, Cn), dtype=torch.float32, device=dev)
+        eps = torch.empty(Cn, dtype=torch.float32, device=dev)
+        io.accepted, io.hamiltonians, io.logp, io.step_sizes = acc.data_ptr(), ham.data_ptr(), lp.data_ptr(), eps.data_ptr()
+    inj_p = _to_dev(inject_momenta, dev)
+    inj_u = _to_dev(inject_uniforms, dev)
+    if inj_p is not None:
+        assert tuple(inj_p.shape) == (num_samples, Cn, d), inj_p.shape
+        io.inject_momenta = inj_p.data_ptr()
+    if inj_u is not None:
+        assert tuple(inj_u.shape) == (num_samples, Cn), inj_u.shape
+        io.inject_uniforms = inj_u.data_ptr()
+    M = len(preps)
+    evals = num_samples * (num_steps + 1) if integrator == INTEGRATOR_LEAPFROG else num_samples * num_steps * 2 * M
+    launches = 0
+    with torch.cuda.device(dev):
+        small = (M == 1 and integrator == INTEGRATOR_LEAPFROG and not force_general and preps[0].spec.model_kind == MODEL_MLP)
+        rc = None
+        if small:
+            rc = lib.vihmc_mlp_sample(C.byref(preps[0].problem), C.byref(cfg), Cn, q0d.data_ptr(), samples.data_ptr(),
+                                      C.byref(io), _stream(dev))
+            if rc == 2:  # VIHMC_ERR_UNSUPPORTED: net too large for the persistent small-MLP kernel
+                rc = None
+            else:
+                launches = 1
+        if rc is None:
+            probs = (_lib.Problem * M)(*[p.problem for p in preps])
+            need = max(int(lib.vihmc_workspace_bytes(C.byref(p.problem), Cn)) for p in preps)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            rc = lib.vihmc_sample(probs, M, C.byref(cfg), Cn, q0d.data_ptr(), samples.data_ptr(), C.byref(io), ws.data_ptr(),
+                                  ws.numel(), _stream(dev))
+            launches = -1  # many; counted by the caller from the launch model if needed
+        _lib.check(rc)
+    res = SampleResult(samples, acc, ham, lp, eps, grad_evals_per_chain=evals, gpu_launches=launches)
+    if to_host:
+        host = lambda t: None if t is None else t.cpu()
+        res = SampleResult(host(samples), host(acc), host(ham), host(lp), host(eps), evals, launches)
+    return res
+
+
+def momentum_philox(seed: int, iteration: int, chain0: int, chains: int, d: int, device=None) -> torch.Tensor:
+    dev = _require_cuda(device)
+    p = torch.empty((chains, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_momentum_philox(seed, iteration, chain0, chains, d, p.data_ptr(), _stream(dev)))
+    return p
+
+
+def uniform_philox(seed: int, iteration: int, chain0: int, chains: int, device=None) -> torch.Tensor:
+    dev = _require_cuda(device)
+    u = torch.empty(chains, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_uniform_philox(seed, iteration, chain0, chains, u.data_ptr(), _stream(dev)))
+    return u
+
+
+def vi_redraw_philox(seed: int, iteration: int, chain0: int, chains: int, mu: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    dev = _require_cuda()
+    mu_d, sg_d = _to_dev(mu, dev), _to_dev(sigma, dev)
+    D = mu_d.numel()
+    W = torch.empty((chains, D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_vi_redraw_philox(seed, iteration, chain0, chains, D, mu_d.data_ptr(), sg_d.data_ptr(),
+                                                      W.data_ptr(), _stream(dev)))
+    return W
+
+
+def scatter_vi(frozen: torch.Tensor, sens_ind, q: torch.Tensor) -> torch.Tensor:
+    dev = _require_cuda()
+    fr = _to_dev(frozen, dev)
+    ind = _to_dev(np.asarray(sens_ind, dtype=np.int64), dev, torch.int64)
+    qd = _to_dev(q, dev)
+    Cn, d = qd.shape
+    W = torch.empty((Cn, fr.numel()), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_scatter_vi(fr.data_ptr(), ind.data_ptr(), qd.data_ptr(), W.data_ptr(), Cn, fr.numel(), d,
+                                                _stream(dev)))
+    return W
+
+
+def leapfrog_update(q: torch.Tensor, p: torch.Tensor, g: torch.Tensor, eps: float, kick: float, drift: float,
+                    eps_per_chain: Optional[torch.Tensor] = None, want_ke: bool = False):
+    """In-place fused update on device tensors q,p [C,d]; returns ke[C] if requested."""
+    dev = _require_cuda(q.device)
+    Cn, d = q.shape
+    lib = _lib.load()
+    ke = scratch = None
+    if want_ke:
+        ke = torch.empty(Cn, dtype=torch.float32, device=dev)
+        scratch = torch.empty(Cn * int(lib.vihmc_ke_partials(d)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.vihmc_leapfrog_update(q.data_ptr(), p.data_ptr(), g.data_ptr(), eps, _ptr(eps_per_chain), kick, drift,
+                                             Cn, d, _ptr(ke), _ptr(scratch), _stream(dev)))
+    return ke
+
+
+def mh_accept(H0, H1, u, q_prop, q_cur, q_fb, stored=None, accepted=None):
+    dev = _require_cuda(q_prop.device)
+    Cn, d = q_prop.shape
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_mh_accept(H0.data_ptr(), H1.data_ptr(), u.data_ptr(), q_prop.data_ptr(), q_cur.data_ptr(),
+                                               q_fb.data_ptr(), _ptr(stored), int(stored is not None), _ptr(accepted), None,
+                                               None, None, Cn, d, _stream(dev)))
