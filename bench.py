@@ -178,7 +178,7 @@ def cpu_baseline_leg():
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(steps, warmup, n_gpus):
+def run_ours(steps, warmup, n_gpus, skip_cpu=False):
     import torch
     import torch.distributed as dist
     from vihmc import engine, samplers
@@ -273,7 +273,7 @@ def run_ours(steps, warmup, n_gpus):
                      "note": "neither hbm nor tensor: 20x10x10 tiles are below any UMMA shape and all state lives in "
                              "shared memory; peak = 148 SM x 128 FMA lanes x 2 x sm_max_mhz (computed, not in "
                              "MEASURED_PEAKS.json); achieved = 14 kFLOP per chain-grad-eval (SURVEY 8(d)) / event time"},
-        "cpu_baseline": cpu_baseline_leg() if world == 1 else None,
+        "cpu_baseline": cpu_baseline_leg() if (world == 1 and not skip_cpu) else None,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
                 "seconds": e2e_s},
         "gpu_launches": 1,
@@ -291,8 +291,9 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     a = ap.parse_args()
-    line = run_reference(a.steps, a.warmup, a.gpus) if a.impl == "reference" else run_ours(a.steps, a.warmup, a.gpus)
+    line = run_reference(a.steps, a.warmup, a.gpus) if a.impl == "reference" else run_ours(a.steps, a.warmup, a.gpus, a.skip_cpu_baseline)
     if line is not None:
         print(json.dumps(line), flush=True)
 
