@@ -1,0 +1,196 @@
+"""GPU parity tests for the dense path (DeepONet and wide MLP) and the large-d building blocks, through the C ABI.
+
+Tolerance: log-posterior and gradient within rtol 1e-5 (fp32), gradient taken relative to its largest component."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import closures as oc
+from oracle import hamiltorch_restated as hr
+from vihmc import engine, samplers, synth
+from vihmc.spec import LogProbSpec, MLPArch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _close(got, ref, rtol=RTOL):
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_deeponet_logp_grad_matches_reference_golden(name):
+    g = cases.load_golden("deeponet_logp_grad.npz")
+    inp = cases.don_inputs(name)
+    # VI-HMC closure (reduced vector)
+    logp, grad = engine.logp_grad(cases.don_spec(inp, "vi"), torch.from_numpy(g[f"{name}/vi/q"]))
+    np.testing.assert_allclose(logp.cpu().numpy(), g[f"{name}/vi/logp"], rtol=RTOL)
+    for i in range(grad.shape[0]):
+        _close(grad[i].cpu().numpy(), g[f"{name}/vi/grad"][i])
+    # full HMC closure and the M=2 split closures
+    q = torch.from_numpy(g[f"{name}/full/q"])
+    logp, grad = engine.logp_grad(cases.don_spec(inp, "full"), q)
+    np.testing.assert_allclose(logp.cpu().numpy(), g[f"{name}/full/logp"], rtol=RTOL)
+    for i in range(grad.shape[0]):
+        _close(grad[i].cpu().numpy(), g[f"{name}/full/grad"][i])
+    for si, sp in enumerate(cases.don_spec(inp, "split")):
+        logp, grad = engine.logp_grad(sp, q)
+        np.testing.assert_allclose(logp.cpu().numpy(), g[f"{name}/split{si}/logp"], rtol=RTOL)
+        for i in range(grad.shape[0]):
+            _close(grad[i].cpu().numpy(), g[f"{name}/split{si}/grad"][i])
+
+
+def test_deeponet_many_chains_and_ragged_tiles_vs_fp64_oracle():
+    """N and P chosen off the 128-tile grid; 9 chains; relu variant as well."""
+    from vihmc.spec import DeepONetArch
+
+    for act in ("tanh", "relu"):
+        arch = DeepONetArch(width_branch=20, width_trunk=24, in_branch=7, depth_branch=3, depth_trunk=3, output_neurons=12, act=act)
+        x1, x2, y, theta = synth.burgers_like(arch, n_train=131, n_t=13, n_x=11, seed=3)
+        spec = LogProbSpec(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
+        closure = oc.DeepONetLogProb(x1=x1.unsqueeze(1), x2=x2.unsqueeze(0), y=y, width_branch=20, width_trunk=24, in_branch=7,
+                                     depth_branch=3, depth_trunk=3, output_neurons=12, act=act, dtype=torch.float64)
+        rs = np.random.RandomState(0)
+        q = (theta.numpy()[None] + 0.02 * rs.randn(9, arch.num_params)).astype(np.float32)
+        logp, grad = engine.logp_grad(spec, torch.from_numpy(q))
+        for c in (0, 4, 8):
+            lp, gr = oc.value_and_grad(closure, torch.from_numpy(q[c]).double())
+            assert abs(float(logp[c]) - float(lp)) <= RTOL * abs(float(lp))
+            _close(grad[c].cpu().numpy(), gr.numpy(), rtol=2e-5)
+
+
+def test_deeponet_predict_matches_oracle():
+    inp = cases.don_inputs("small")
+    spec = cases.don_spec(inp, "vi")
+    g = cases.load_golden("deeponet_logp_grad.npz")
+    q = torch.from_numpy(g["small/vi/q"])
+    pred = engine.predict(spec, q).cpu()
+    closure = cases.don_oracle(inp, "vi", dtype=torch.float64)
+    for i in range(len(q)):
+        ref = closure.forward(q[i].double())
+        np.testing.assert_allclose(pred[i].numpy(), ref.detach().numpy(), rtol=2e-5, atol=2e-6)
+    # predict_model on "validation" data = a different slice of operator data
+    vx1, vx2, vy, _ = synth.burgers_like(inp["arch"], n_train=4, n_t=5, n_x=7, seed=9)
+    out, logps = samplers.predict_model(spec, q, data=(vx1.unsqueeze(1), vx2.unsqueeze(0), vy))
+    assert out.shape == (3, 4, 35) and len(logps) == 3
+
+
+def test_general_sampler_deeponet_leapfrog_vs_oracle():
+    inp = cases.don_inputs("small")
+    spec = cases.don_spec(inp, "vi")
+    closure = cases.don_oracle(inp, "vi", dtype=torch.float64)
+    d, S, L, eps = spec.d, 4, 6, 1e-3
+    rs = np.random.RandomState(1)
+    q0 = torch.from_numpy((inp["mu"].numpy()[inp["ind"]][None] + 0.01 * rs.randn(3, d)).astype(np.float32))
+    p = torch.from_numpy(rs.randn(S, 3, d).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(0.2, 1.0, size=(S, 3)).astype(np.float32))
+    res = engine.run_sampler([spec], q0, S, L, eps, inject_momenta=p, inject_uniforms=u)
+    for c in range(3):
+        tr = {}
+        out = hr.sample(closure, q0[c].double(), num_samples=S, num_steps_per_sample=L, step_size=eps, momenta=p[:, c].double(),
+                        uniforms=u[:, c], trace=tr)
+        np.testing.assert_allclose(res.hamiltonians[:, c, 0].numpy(), tr["H0"], rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(res.hamiltonians[:, c, 1].numpy(), tr["H1"], rtol=1e-5, atol=1e-3)
+        assert [bool(a) for a in res.accepted[:, c].numpy()] == tr["accept"]
+        np.testing.assert_allclose(res.samples[:, c].numpy(), torch.stack(out).numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_split_integrator_vs_oracle():
+    """Integrator.SPLITTING with M = 2 closures (main_HMC_splitting.py:367-369) against the restated integrator."""
+    inp = cases.don_inputs("small")
+    specs = cases.don_spec(inp, "split")
+    closures = cases.don_oracle(inp, "split", dtype=torch.float64)
+    D, S, L, eps = specs[0].d, 3, 4, 5e-4
+    rs = np.random.RandomState(4)
+    q0 = torch.from_numpy((inp["theta"].numpy()[None] + 0.01 * rs.randn(2, D)).astype(np.float32))
+    p = torch.from_numpy(rs.randn(S, 2, D).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(0.2, 1.0, size=(S, 2)).astype(np.float32))
+    out = samplers.sample(specs, q0, num_samples=S, num_steps_per_sample=L, step_size=eps, integrator=samplers.Integrator.SPLITTING,
+                          inject_momenta=p, inject_uniforms=u, return_result=True)
+    for c in range(2):
+        tr = {}
+        ref = hr.sample(closures, q0[c].double(), num_samples=S, num_steps_per_sample=L, step_size=eps,
+                        integrator=hr.Integrator.SPLITTING, momenta=p[:, c].double(), uniforms=u[:, c], trace=tr)
+        np.testing.assert_allclose(out.hamiltonians[:, c, 0].numpy(), tr["H0"], rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(out.hamiltonians[:, c, 1].numpy(), tr["H1"], rtol=1e-5, atol=1e-3)
+        assert [bool(a) for a in out.accepted[:, c].numpy()] == tr["accept"]
+        np.testing.assert_allclose(out.samples[:, c].numpy(), torch.stack(ref).numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_wide_mlp_dense_path_vs_oracle():
+    """An MLP wider than the small-net kernel's range (64 > 32) goes through the GEMM path; cfg5's shape in miniature."""
+    arch = MLPArch(in_dim=1, widths=(64, 48, 64), out_dim=1, act="tanh", last_bias=True)
+    x, y = synth.wide_bnn_data(n=333, seed=0)
+    spec = LogProbSpec(arch=arch, x=x, y=y, loss="NLL", tau_out=0.0025, prior_sigma_scalar=1.0)
+    closure = oc.BnnLogProb(x=x, y=y, widths=(64, 48, 64), loss="NLL", tau_out=0.0025,
+                            prior=("sliced", [1.0] * len(arch.tensor_numels())), dtype=torch.float64)
+    q = synth.default_linear_init(arch, seed=1).unsqueeze(0).repeat(3, 1)
+    q[1:] += 0.05 * torch.from_numpy(np.random.RandomState(2).randn(2, arch.num_params).astype(np.float32))
+    logp, grad = engine.logp_grad(spec, q)
+    for c in range(3):
+        lp, gr = oc.value_and_grad(closure, q[c].double())
+        assert abs(float(logp[c]) - float(lp)) <= RTOL * abs(float(lp))
+        _close(grad[c].cpu().numpy(), gr.numpy(), rtol=2e-5)
+    pred = engine.predict(spec, q).cpu()
+    np.testing.assert_allclose(pred[0].numpy(), closure.forward(q[0].double()).detach().numpy()[:, 0], rtol=2e-5, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# building blocks of the large-d path
+# ---------------------------------------------------------------------------------------------
+def test_scatter_and_redraw():
+    rs = np.random.RandomState(0)
+    D, d, Cn = 1001, 77, 5
+    frozen = torch.from_numpy(rs.randn(D).astype(np.float32))
+    ind = np.sort(rs.choice(D, d, replace=False)).astype(np.int64)
+    q = torch.from_numpy(rs.randn(Cn, d).astype(np.float32))
+    W = engine.scatter_vi(frozen, ind, q).cpu()
+    ref = frozen[None].repeat(Cn, 1)
+    ref[:, ind] = q
+    assert torch.equal(W, ref)
+    # VI redraw hook (my_make_func.py:45-46): w = mu + sigma * z with the Philox stream 2
+    from oracle import philox_ref
+    sigma = torch.from_numpy((0.01 + rs.rand(D)).astype(np.float32))
+    Wr = engine.vi_redraw_philox(11, 3, 2, Cn, frozen, sigma).cpu().numpy()
+    z = philox_ref.normals(11, 2, Cn, 3, D, stream=2)
+    np.testing.assert_allclose(Wr, frozen.numpy()[None] + sigma.numpy()[None] * z, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("d", [1, 40, 4097, 172401])
+def test_leapfrog_update_bitwise_vs_torch(d):
+    """p += kick*eps*g; q += drift*eps*p with torch's rounding (separate mul and add), ragged d, per-chain eps."""
+    rs = np.random.RandomState(d)
+    Cn = 3
+    q = torch.from_numpy(rs.randn(Cn, d).astype(np.float32)).cuda()
+    p = torch.from_numpy(rs.randn(Cn, d).astype(np.float32)).cuda()
+    g = torch.from_numpy((100 * rs.randn(Cn, d)).astype(np.float32)).cuda()
+    eps = torch.tensor([1e-4, 3e-4, 7e-5], device="cuda")
+    for kick, drift in ((0.5, 1.0), (1.0, 1.0), (1.0, 0.0), (-0.5, 0.0)):
+        q_ref, p_ref = q.clone(), p.clone()
+        p_ref = p_ref + (kick * eps)[:, None] * g
+        if drift != 0.0:
+            q_ref = q_ref + (drift * eps)[:, None] * p_ref
+        ke = engine.leapfrog_update(q, p, g, 0.0, kick, drift, eps_per_chain=eps, want_ke=True)
+        assert torch.equal(p, p_ref) and torch.equal(q, q_ref)
+        np.testing.assert_allclose(ke.cpu().numpy(), 0.5 * (p_ref.double() ** 2).sum(1).cpu().numpy(), rtol=2e-6)
+
+
+def test_mh_accept_select():
+    rs = np.random.RandomState(0)
+    Cn, d = 6, 5000
+    H0 = torch.tensor([1.0, 1.0, 1.0, float("nan"), 1.0, 5.0], device="cuda")
+    H1 = torch.tensor([0.5, 2.0, 2.0, 1.0, float("inf"), 5.0], device="cuda")
+    u = torch.tensor([0.9, 0.9, 0.1, 0.5, 0.5, 1.0 - 6e-8], device="cuda")  # rho: 0, -1, -1, nan, -inf, 0
+    want = [1, 0, 1, 0, 0, 1]
+    q_prop = torch.from_numpy(rs.randn(Cn, d).astype(np.float32)).cuda()
+    q_cur = torch.zeros_like(q_prop)
+    q_fb = torch.from_numpy(rs.randn(Cn, d).astype(np.float32)).cuda()
+    fb0 = q_fb.clone()
+    stored = torch.empty_like(q_prop)
+    acc = torch.empty(Cn, dtype=torch.uint8, device="cuda")
+    engine.mh_accept(H0, H1, u, q_prop, q_cur, q_fb, stored=stored, accepted=acc)
+    assert acc.cpu().tolist() == want
+    for c, a in enumerate(want):
+        exp = q_prop[c] if a else fb0[c]
+        assert torch.equal(q_cur[c], exp) and torch.equal(stored[c], exp) and torch.equal(q_fb[c], exp)

@@ -1,13 +1,616 @@
-// Dense path (DeepONet, wide MLP) -- placeholder until the GEMM kernels land.
+// Dense path: DeepONet (branch, trunk, dot-product head) and wide-MLP log-posterior + gradient for
+// C chains at once, as batched GEMMs with fused epilogues.
+//
+// Restates, per chain, the reference closures
+//   Operator_network/VI_HMC/main_VI_HMC_burgers.py:86-178 (prior :96-102, likelihood :157-163)
+//   Operator_network/VI_HMC/my_make_func.py:44-83 (scatter :48-50, branch :53-61, feature layer :33-36,63-65,
+//                                                  trunk :69-77, head einsum :79, + scalar bias :81-82)
+//   Operator_network/HMC/main_HMC_splitting.py:134-204 (same arithmetic, `reshape` instead of `squeeze`)
+// and the autograd backward hamiltorch takes through them.
+//
+// Round-1 kernels are FP32 SIMT (register-tiled 128x128x8 SGEMM, FP32 accumulate): the correctness
+// baseline every later tensor-core kernel is checked against.  Reductions are fixed-order (per-CTA
+// partials + a second pass), never float atomics, so accept/reject is reproducible.
+//
+// Data layout in HBM for one batch of Cb chains (all fp32, row-major):
+//   Wf  [Cb, D]            full weights (VI scatter of q into the frozen means)
+//   act_a[l] [Cb, N, w]    branch activations after layer l;  act_b[l] [Cb, P, w] trunk activations
+//   G   [Cb, N, P]         d loglik / d output (the only [N,P]-sized per-chain buffer)
+//   dz0/dz1 [Cb, R, w]     ping-pong pre-activation gradients, R = max(N, P)
+//   dWf [Cb, D]            gradient w.r.t. the full weight vector; gathered to grad[C, d] at the end
 #include "common.cuh"
 
 namespace vihmc {
-bool dense_supported(const vihmc_problem*) { return false; }
-size_t dense_workspace_bytes(const vihmc_problem*, long long) { return 0; }
-int dense_logp_grad(const vihmc_problem*, long long, const float*, float*, float*, void*, size_t, cudaStream_t) {
-  return fail(VIHMC_ERR_UNSUPPORTED, "dense path not built");
+
+int launch_scatter(const float*, const long long*, const float*, float*, long long, long long, long long, cudaStream_t);
+
+// =============================================================================================
+// batched SGEMM  C[b] = opA(A[b]) (MxK) * opB(B[b]) (KxN), generic element strides, fused epilogues
+// =============================================================================================
+enum Epilogue {
+  EPI_STORE = 0,      // C = acc
+  EPI_BIAS_ACT = 1,   // C = act(acc + bias[n])           (act = identity when act < 0)
+  EPI_DACT = 2,       // C = acc * act'(aux[m,n])         (aux = the layer's stored activation)
+  EPI_HEAD = 3        // r = acc + bias0 - Y[m,n]; C = -prec r; partial sums of loglik and of C per CTA
+};
+
+struct GemmArgs {
+  const float* A; long long a_bs, a_sm, a_sk;
+  const float* B; long long b_bs, b_sk, b_sn;
+  float* C; long long c_bs, ldc;
+  int M, N, K;
+  // epilogue operands
+  const float* bias; long long bias_bs;   // [N] per batch (EPI_BIAS_ACT) or scalar per batch (EPI_HEAD)
+  const float* aux; long long aux_bs, ld_aux;  // activation (EPI_DACT) or Y (EPI_HEAD; aux_bs = 0: shared)
+  int act;
+  float ll_const, half_prec, prec;
+  float* part_ll; float* part_g;          // [batch, tiles] (EPI_HEAD)
+};
+
+constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8, GEMM_THREADS = 256;
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) sgemm_batched_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* __restrict__ A = g.A + (long long)b * g.a_bs;
+  const float* __restrict__ B = g.B + (long long)b * g.b_bs;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;  // thread's 8x8 micro-tile: rows ty*8.., cols tx*8..
+
+  // loader mapping: make the unit-stride dimension the fastest-varying one across threads
+  const bool a_kfast = g.a_sk == 1;
+  const bool b_nfast = g.b_sn == 1;
+  int a_m[4], a_k[4], b_k[4], b_n[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * GEMM_THREADS;  // 0..1023 = BM*BK
+    if (a_kfast) { a_k[i] = e % BK; a_m[i] = e / BK; } else { a_m[i] = e % BM; a_k[i] = e / BM; }
+    if (b_nfast) { b_n[i] = e % BN; b_k[i] = e / BN; } else { b_k[i] = e % BK; b_n[i] = e / BK; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + a_m[i], k = k0 + a_k[i];
+      ra[i] = (m < g.M && k < g.K) ? __ldg(A + (long long)m * g.a_sm + (long long)k * g.a_sk) : 0.0f;
+      const int kk = k0 + b_k[i], n = n0 + b_n[i];
+      rb[i] = (kk < g.K && n < g.N) ? __ldg(B + (long long)kk * g.b_sk + (long long)n * g.b_sn) : 0.0f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[buf][a_k[i]][a_m[i]] = ra[i];
+      Bs[buf][b_k[i]][b_n[i]] = rb[i];
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  const int nk = (g.K + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TM], bv[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + 4]);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      stash(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---------------- epilogue ----------------
+  float* __restrict__ Cb = g.C + (long long)b * g.c_bs;
+  float ll_acc = 0.0f, g_acc = 0.0f;
+  const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)b * g.bias_bs) : 0.0f;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (EPI == EPI_BIAS_ACT) {
+        v += __ldg(g.bias + (long long)b * g.bias_bs + n);
+        if (g.act == VIHMC_ACT_TANH) v = tanhf(v);
+        else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+      } else if (EPI == EPI_DACT) {
+        const float a = __ldg(g.aux + (long long)b * g.aux_bs + (long long)m * g.ld_aux + n);
+        v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - a * a) : (a > 0.0f ? 1.0f : 0.0f);
+      } else if (EPI == EPI_HEAD) {
+        const float r = v + bias0 - __ldg(g.aux + (long long)b * g.aux_bs + (long long)m * g.ld_aux + n);
+        ll_acc += g.ll_const - g.half_prec * r * r;
+        v = -g.prec * r;
+        g_acc += v;
+      }
+      Cb[(long long)m * g.ldc + n] = v;
+    }
+  }
+  if (EPI == EPI_HEAD) {
+    __shared__ float red[2][GEMM_THREADS / 32];
+    ll_acc = warp_sum(ll_acc);
+    g_acc = warp_sum(g_acc);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = ll_acc; red[1][tid >> 5] = g_acc; }
+    __syncthreads();
+    if (tid == 0) {
+      float s0 = 0.0f, s1 = 0.0f;
+      for (int w = 0; w < GEMM_THREADS / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+      const long long tiles = (long long)gridDim.x * gridDim.y;
+      const long long t = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+      g.part_ll[(long long)b * tiles + t] = s0;
+      g.part_g[(long long)b * tiles + t] = s1;
+    }
+  }
 }
-int dense_predict(const vihmc_problem*, long long, const float*, float*, void*, size_t, cudaStream_t) {
-  return fail(VIHMC_ERR_UNSUPPORTED, "dense path not built");
+
+template <int EPI>
+static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
+  if (g.M < 1 || g.N < 1 || g.K < 1 || batch < 1) return fail(VIHMC_ERR_INVALID, "gemm: empty problem");
+  if (batch > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch > 65535");
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
+  sgemm_batched_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
+  VIHMC_LAUNCH_OK("sgemm_batched_kernel");
+  return VIHMC_OK;
 }
+
+// =============================================================================================
+// small helper kernels
+// =============================================================================================
+// trunk features [t, sin 2pi x, sin 4pi x, cos 2pi x, cos 4pi x]  (my_make_func.py:33-36,63-65)
+__global__ void trunk_features_kernel(const float* __restrict__ x2, long long P, float* __restrict__ F) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float t = x2[2 * p], x = x2[2 * p + 1];
+  const float two_pi = 6.283185307179586f;   // float32(2*np.pi) as torch computes 2*np.pi*x in fp32
+  const float four_pi = 12.566370614359172f;
+  F[5 * p + 0] = t;
+  F[5 * p + 1] = sinf(two_pi * x);
+  F[5 * p + 2] = sinf(four_pi * x);
+  F[5 * p + 3] = cosf(two_pi * x);
+  F[5 * p + 4] = cosf(four_pi * x);
+}
+
+// out[b, n] = sum_r Z[b, r, n]   (bias gradients).  grid (ceil(n/32), batch), block (32, 8)
+__global__ void colsum_kernel(const float* __restrict__ Z, long long z_bs, long long R, int ncols, long long ldz,
+                              float* __restrict__ out, long long out_bs) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (col < ncols)
+    for (long long r = threadIdx.y; r < R; r += 8) s += Z[(long long)b * z_bs + r * ldz + col];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < ncols) {
+    float t = 0.0f;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[(long long)b * out_bs + col] = t;
+  }
+}
+
+// fixed-order sum of per-tile partials: out[b] = sum_t part[b, t]  (one warp per batch row)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, long long tiles, long long batch, float* __restrict__ out,
+                                       long long out_stride) {
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= batch) return;
+  float s = 0.0f;
+  for (long long t = threadIdx.x & 31; t < tiles; t += 32) s += part[b * tiles + t];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[b * out_stride] = s;
+}
+
+// MLP likelihood on the output column: G[b,n] = -prec (o - y); per-CTA partial loglik.  grid (ceil(N/256), batch)
+__global__ void mlp_loss_kernel(const float* __restrict__ O, const float* __restrict__ y, long long N, float ll_const,
+                                float half_prec, float prec, float* __restrict__ G, float* __restrict__ part_ll) {
+  const int b = blockIdx.y;
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float ll = 0.0f;
+  if (n < N) {
+    const float r = O[(long long)b * N + n] - __ldg(y + n);
+    ll = ll_const - half_prec * r * r;
+    G[(long long)b * N + n] = -prec * r;
+  }
+  __shared__ float red[8];
+  ll = warp_sum(ll);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    part_ll[(long long)b * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// grad[c,i] = dWf[c, ind[i]] - (q - mu) / sigma^2 / prior_scale ; logp[c] = loglik[c] + (sum_i -0.5 (q-mu)^2/sigma^2 + log_norm)/scale
+// one CTA per chain; fixed-order block reduction of the prior.
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ dWf, const long long* __restrict__ ind,
+                                                        const float* __restrict__ q, const float* __restrict__ prior_mu,
+                                                        const float* __restrict__ prior_sigma, float sigma_scalar,
+                                                        float inv_scale, float log_norm, const float* __restrict__ loglik,
+                                                        long long D, long long d, float* __restrict__ logp,
+                                                        float* __restrict__ grad) {
+  const long long c = blockIdx.x;
+  float lp = 0.0f;
+  for (long long i = threadIdx.x; i < d; i += blockDim.x) {
+    const float sg = prior_sigma ? __ldg(prior_sigma + i) : sigma_scalar;
+    const float iv = isinf(sg) ? 0.0f : 1.0f / (sg * sg);
+    const float dq = q[c * d + i] - (prior_mu ? __ldg(prior_mu + i) : 0.0f);
+    lp = fmaf(-0.5f * dq * dq, iv, lp);
+    if (grad != nullptr) {
+      const long long f = ind ? __ldg(ind + i) : i;
+      grad[c * d + i] = fmaf(-dq * iv, inv_scale, dWf[c * D + f]);
+    }
+  }
+  __shared__ float red[8];
+  lp = warp_sum(lp);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    logp[c] = loglik[c] + (s + log_norm) * inv_scale;
+  }
+}
+
+// =============================================================================================
+// host orchestration
+// =============================================================================================
+struct Stack {
+  int n_layers, in_dim;
+  int dims[VIHMC_MAX_LAYERS];
+  long long w_off[VIHMC_MAX_LAYERS], b_off[VIHMC_MAX_LAYERS];
+  bool has_bias[VIHMC_MAX_LAYERS];
+  int in_of(int l) const { return l == 0 ? in_dim : dims[l - 1]; }
+  int max_width() const {
+    int w = 0;
+    for (int l = 0; l < n_layers; ++l) w = dims[l] > w ? dims[l] : w;
+    return w;
+  }
+};
+
+static long long build_stack(Stack& s, int n_layers, int in_dim, const int32_t* dims, long long off, bool last_bias) {
+  s.n_layers = n_layers;
+  s.in_dim = in_dim;
+  for (int l = 0; l < n_layers; ++l) {
+    s.dims[l] = dims[l];
+    s.w_off[l] = off;
+    off += (long long)dims[l] * s.in_of(l);
+    s.has_bias[l] = (l < n_layers - 1) || last_bias;
+    s.b_off[l] = off;
+    if (s.has_bias[l]) off += dims[l];
+  }
+  return off;
+}
+
+struct DensePlan {
+  bool deeponet;
+  Stack a, b;       // MLP: a only
+  long long D, N, P, R;
+  int K;            // DeepONet: output_neurons
+  long long head_tiles, loss_tiles;
+  // per-chain float counts
+  long long act_a_floats, act_b_floats, per_chain_floats;
+  long long shared_floats;  // trunk features
+};
+
+static int make_plan(const vihmc_problem* p, DensePlan& pl) {
+  pl.deeponet = p->model_kind == VIHMC_MODEL_DEEPONET;
+  pl.N = p->N;
+  pl.P = pl.deeponet ? p->P : 1;
+  long long off;
+  if (pl.deeponet) {
+    off = build_stack(pl.a, p->n_layers_a, p->in_a, p->dims_a, 1, true);
+    off = build_stack(pl.b, p->n_layers_b, p->in_b, p->dims_b, off, true);
+    pl.K = p->dims_a[p->n_layers_a - 1];
+    if (p->dims_b[p->n_layers_b - 1] != pl.K) return fail(VIHMC_ERR_INVALID, "branch and trunk output widths differ");
+    if (p->impose_bc && p->in_b != 5) return fail(VIHMC_ERR_INVALID, "impose_bc needs in_trunk = 5");
+  } else {
+    off = build_stack(pl.a, p->n_layers_a, p->in_a, p->dims_a, 0, p->last_bias != 0);
+    pl.b.n_layers = 0;
+    pl.K = 1;
+    if (p->dims_a[p->n_layers_a - 1] != 1) return fail(VIHMC_ERR_UNSUPPORTED, "dense MLP path needs out_dim = 1");
+  }
+  if (off != p->D) return fail(VIHMC_ERR_INVALID, "D=%lld does not match the architecture (%lld)", (long long)p->D, off);
+  pl.D = p->D;
+  pl.R = pl.N > pl.P ? pl.N : pl.P;
+  pl.act_a_floats = 0;
+  for (int l = 0; l < pl.a.n_layers; ++l) pl.act_a_floats += pl.N * pl.a.dims[l];
+  pl.act_b_floats = 0;
+  for (int l = 0; l < pl.b.n_layers; ++l) pl.act_b_floats += pl.P * pl.b.dims[l];
+  const int wmax = pl.a.max_width() > pl.b.max_width() ? pl.a.max_width() : pl.b.max_width();
+  pl.head_tiles = ((pl.P + BN - 1) / BN) * ((pl.N + BM - 1) / BM);
+  pl.loss_tiles = (pl.N + 255) / 256;
+  const long long tiles = pl.deeponet ? pl.head_tiles : pl.loss_tiles;
+  const long long G = pl.deeponet ? pl.N * pl.P : pl.N;
+  pl.per_chain_floats = 2 * pl.D + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P;
+  pl.shared_floats = pl.deeponet ? pl.P * 5 + 64 : 64;
+  return VIHMC_OK;
+}
+
+bool dense_supported(const vihmc_problem* p) {
+  if (p->act == VIHMC_ACT_SINE) return false;  // the dense path stores activations only; cos(z) would need z
+  DensePlan pl;
+  return make_plan(p, pl) == VIHMC_OK;
+}
+
+static const long long kMaxBatchBytes = 40LL << 30;  // cap one chain batch at 40 GB of workspace
+
+static long long chains_per_batch(const DensePlan& pl, long long C, size_t avail_bytes) {
+  const long long per = pl.per_chain_floats * 4;
+  long long cb = (long long)(avail_bytes / (size_t)per);
+  if (cb > C) cb = C;
+  if (cb > 65535) cb = 65535;
+  return cb;
+}
+
+size_t dense_workspace_bytes(const vihmc_problem* p, long long C) {
+  DensePlan pl;
+  if (make_plan(p, pl) != VIHMC_OK) return 0;
+  const long long per = pl.per_chain_floats * 4;
+  long long cb = kMaxBatchBytes / per;
+  if (cb < 1) cb = 1;
+  if (cb > C) cb = C;
+  return (size_t)(cb * per + pl.shared_floats * 4 + 4096);
+}
+
+namespace {
+struct Bump {
+  float* base;
+  long long off = 0;
+  explicit Bump(float* b) : base(b) {}
+  float* take(long long n) {
+    off = (off + 63) / 64 * 64;
+    float* r = base + off;
+    off += n;
+    return r;
+  }
+};
+}  // namespace
+
+// forward of one stack for Cb chains: in [R, in_dim] shared -> acts[l] [Cb, R, dims[l]]
+static int stack_forward(const Stack& s, const float* input, long long R, const float* Wf, long long D, float* const* acts,
+                         int act, bool act_on_last, int Cb, cudaStream_t st) {
+  for (int l = 0; l < s.n_layers; ++l) {
+    GemmArgs g{};
+    const int in = s.in_of(l), out = s.dims[l];
+    g.A = l == 0 ? input : acts[l - 1];
+    g.a_bs = l == 0 ? 0 : R * in; g.a_sm = in; g.a_sk = 1;
+    g.B = Wf + s.w_off[l]; g.b_bs = D; g.b_sk = 1; g.b_sn = in;   // opB[k,n] = W[n,k]
+    g.C = acts[l]; g.c_bs = R * out; g.ldc = out;
+    g.M = (int)R; g.N = out; g.K = in;
+    const bool last = l == s.n_layers - 1;
+    if (s.has_bias[l]) {
+      g.bias = Wf + s.b_off[l]; g.bias_bs = D;
+      g.act = (last && !act_on_last) ? -1 : act;
+      if (int rc = launch_gemm<EPI_BIAS_ACT>(g, Cb, st)) return rc;
+    } else {
+      if (int rc = launch_gemm<EPI_STORE>(g, Cb, st)) return rc;
+    }
+  }
+  return VIHMC_OK;
+}
+
+// backward of one stack: dz holds d/d(pre-activation of the last layer) [Cb, R, dims[last]] on entry.
+static int stack_backward(const Stack& s, const float* input, long long R, const float* Wf, float* dWf, long long D,
+                          float* const* acts, float* dz_cur, float* dz_other, int act, int Cb, cudaStream_t st) {
+  for (int l = s.n_layers - 1; l >= 0; --l) {
+    const int in = s.in_of(l), out = s.dims[l];
+    // dW[o,i] = sum_r dz[r,o] * a_in[r,i]
+    GemmArgs g{};
+    g.A = dz_cur; g.a_bs = R * out; g.a_sm = 1; g.a_sk = out;            // opA[m=o,k=r] = dz[r,o]
+    g.B = l == 0 ? input : acts[l - 1]; g.b_bs = l == 0 ? 0 : R * in; g.b_sk = in; g.b_sn = 1;
+    g.C = dWf + s.w_off[l]; g.c_bs = D; g.ldc = in;
+    g.M = out; g.N = in; g.K = (int)R;
+    if (int rc = launch_gemm<EPI_STORE>(g, Cb, st)) return rc;
+    if (s.has_bias[l]) {
+      colsum_kernel<<<dim3((out + 31) / 32, Cb), dim3(32, 8), 0, st>>>(dz_cur, R * out, R, out, out, dWf + s.b_off[l], D);
+      VIHMC_LAUNCH_OK("colsum_kernel");
+    }
+    if (l > 0) {
+      // dz_prev[r,i] = (sum_o dz[r,o] W[o,i]) * act'(a_{l-1}[r,i])
+      GemmArgs h{};
+      h.A = dz_cur; h.a_bs = R * out; h.a_sm = out; h.a_sk = 1;
+      h.B = Wf + s.w_off[l]; h.b_bs = D; h.b_sk = in; h.b_sn = 1;       // opB[k=o,n=i] = W[o,i]
+      h.C = dz_other; h.c_bs = R * in; h.ldc = in;
+      h.M = (int)R; h.N = in; h.K = out;
+      h.aux = acts[l - 1]; h.aux_bs = R * in; h.ld_aux = in; h.act = act;
+      if (int rc = launch_gemm<EPI_DACT>(h, Cb, st)) return rc;
+      float* t = dz_cur; dz_cur = dz_other; dz_other = t;
+    }
+  }
+  return VIHMC_OK;
+}
+
+static int dense_run(const vihmc_problem* p, long long C, const float* q, float* logp, float* grad, float* predict_out, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  DensePlan pl;
+  if (int rc = make_plan(p, pl)) return rc;
+  if (p->act == VIHMC_ACT_SINE) return fail(VIHMC_ERR_UNSUPPORTED, "dense path implements tanh and relu (the DeepONet reference's set)");
+  if (p->x == nullptr || p->y == nullptr || (pl.deeponet && p->x2 == nullptr)) return fail(VIHMC_ERR_INVALID, "x, x2, y must be device pointers");
+  if ((p->frozen == nullptr) != (p->sens_ind == nullptr)) return fail(VIHMC_ERR_INVALID, "frozen and sens_ind must be given together");
+  if (p->sens_ind == nullptr && p->d != p->D) return fail(VIHMC_ERR_INVALID, "d != D requires sens_ind");
+  if (p->prior_scale == 0.0f) return fail(VIHMC_ERR_INVALID, "prior_scale must be non-zero");
+  if (ws == nullptr) return fail(VIHMC_ERR_WORKSPACE, "dense path needs a workspace");
+  const size_t shared_bytes = (size_t)pl.shared_floats * 4 + 2048;
+  if (ws_bytes <= shared_bytes) return fail(VIHMC_ERR_WORKSPACE, "workspace too small");
+  const long long cb_max = chains_per_batch(pl, C, ws_bytes - shared_bytes);
+  if (cb_max < 1) return fail(VIHMC_ERR_WORKSPACE, "workspace too small for one chain: need %lld bytes", pl.per_chain_floats * 4 + (long long)shared_bytes);
+  const Likelihood lik = make_likelihood(p->loss, p->tau_out);
+  const long long D = pl.D, d = p->d, N = pl.N, P = pl.P;
+  const int wmax = pl.a.max_width() > pl.b.max_width() ? pl.a.max_width() : pl.b.max_width();
+
+  Bump bump(static_cast<float*>(ws));
+  float* feats = nullptr;
+  const float* trunk_in = nullptr;
+  if (pl.deeponet) {
+    if (p->impose_bc) {
+      feats = bump.take(P * 5);
+      trunk_features_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(p->x2, P, feats);
+      VIHMC_LAUNCH_OK("trunk_features_kernel");
+      trunk_in = feats;
+    } else {
+      trunk_in = p->x2;
+    }
+  }
+  float* batch_base = bump.take(0);
+
+  for (long long c0 = 0; c0 < C; c0 += cb_max) {
+    const int Cb = (int)((C - c0) < cb_max ? (C - c0) : cb_max);
+    Bump bb(batch_base);
+    float* Wf = bb.take((long long)Cb * D);
+    float* dWf = bb.take((long long)Cb * D);
+    float* acts_a[VIHMC_MAX_LAYERS];
+    float* acts_b[VIHMC_MAX_LAYERS];
+    for (int l = 0; l < pl.a.n_layers; ++l) acts_a[l] = bb.take((long long)Cb * N * pl.a.dims[l]);
+    for (int l = 0; l < pl.b.n_layers; ++l) acts_b[l] = bb.take((long long)Cb * P * pl.b.dims[l]);
+    const long long tiles = pl.deeponet ? pl.head_tiles : pl.loss_tiles;
+    float* G = nullptr;
+    if (predict_out == nullptr || !pl.deeponet) G = bb.take((long long)Cb * (pl.deeponet ? N * P : N));
+    float* dz0 = bb.take((long long)Cb * pl.R * wmax);
+    float* dz1 = bb.take((long long)Cb * pl.R * wmax);
+    float* part_ll = bb.take((long long)Cb * tiles);
+    float* part_g = bb.take((long long)Cb * tiles);
+    float* loglik = bb.take(Cb);
+    const float* qb = q + c0 * d;
+
+    if (int rc = launch_scatter(p->frozen, reinterpret_cast<const long long*>(p->sens_ind), qb, Wf, Cb, D, d, st)) return rc;
+    if (int rc = stack_forward(pl.a, p->x, N, Wf, D, acts_a, p->act, false, Cb, st)) return rc;
+    if (pl.deeponet)
+      if (int rc = stack_forward(pl.b, trunk_in, P, Wf, D, acts_b, p->act, false, Cb, st)) return rc;
+
+    if (pl.deeponet) {
+      // head: O = Bout * Tout^T + b0 ; fused residual / loglik partials
+      const float* Bout = acts_a[pl.a.n_layers - 1];
+      const float* Tout = acts_b[pl.b.n_layers - 1];
+      const int K = pl.K;
+      GemmArgs g{};
+      g.A = Bout; g.a_bs = N * K; g.a_sm = K; g.a_sk = 1;
+      g.B = Tout; g.b_bs = P * K; g.b_sk = 1; g.b_sn = K;
+      g.M = (int)N; g.N = (int)P; g.K = K;
+      if (predict_out != nullptr) return fail(VIHMC_ERR_INVALID, "internal: DeepONet predict goes through dense_predict");
+      g.C = G; g.c_bs = N * P; g.ldc = P;
+      g.bias = Wf; g.bias_bs = D;                    // scalar output bias is W[0] (my_make_func.py:52)
+      g.aux = p->y; g.aux_bs = 0; g.ld_aux = P;
+      g.ll_const = lik.ll_const; g.half_prec = lik.half_prec; g.prec = lik.prec;
+      g.part_ll = part_ll; g.part_g = part_g;
+      if (int rc = launch_gemm<EPI_HEAD>(g, Cb, st)) return rc;
+      reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, tiles, Cb, loglik, 1);
+      if (grad != nullptr) {
+        reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_g, tiles, Cb, dWf, D);  // d/d b0 = sum G
+        // dBout[n,k] = sum_p G[n,p] Tout[p,k]
+        GemmArgs h{};
+        h.A = G; h.a_bs = N * P; h.a_sm = P; h.a_sk = 1;
+        h.B = Tout; h.b_bs = P * K; h.b_sk = K; h.b_sn = 1;
+        h.C = dz0; h.c_bs = N * K; h.ldc = K; h.M = (int)N; h.N = K; h.K = (int)P;
+        if (int rc = launch_gemm<EPI_STORE>(h, Cb, st)) return rc;
+        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st)) return rc;
+        // dTout[p,k] = sum_n G[n,p] Bout[n,k]
+        GemmArgs t{};
+        t.A = G; t.a_bs = N * P; t.a_sm = 1; t.a_sk = P;
+        t.B = Bout; t.b_bs = N * K; t.b_sk = K; t.b_sn = 1;
+        t.C = dz0; t.c_bs = P * K; t.ldc = K; t.M = (int)P; t.N = K; t.K = (int)N;
+        if (int rc = launch_gemm<EPI_STORE>(t, Cb, st)) return rc;
+        if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, D, acts_b, dz0, dz1, p->act, Cb, st)) return rc;
+      }
+    } else {
+      const float* O = acts_a[pl.a.n_layers - 1];
+      if (predict_out != nullptr) {
+        VIHMC_CUDA_OK(cudaMemcpyAsync(predict_out + c0 * N, O, sizeof(float) * Cb * N, cudaMemcpyDeviceToDevice, st));
+        continue;
+      }
+      mlp_loss_kernel<<<dim3((unsigned)pl.loss_tiles, Cb), 256, 0, st>>>(O, p->y, N, lik.ll_const, lik.half_prec, lik.prec, dz0, part_ll);
+      VIHMC_LAUNCH_OK("mlp_loss_kernel");
+      reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, tiles, Cb, loglik, 1);
+      if (grad != nullptr)
+        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st)) return rc;
+    }
+    finalize_kernel<<<Cb, 256, 0, st>>>(dWf, reinterpret_cast<const long long*>(p->sens_ind), qb, p->prior_mu, p->prior_sigma,
+                                        p->prior_sigma_scalar, 1.0f / p->prior_scale, p->prior_log_norm, loglik, D, d,
+                                        logp + c0, grad ? grad + c0 * d : nullptr);
+    VIHMC_LAUNCH_OK("finalize_kernel");
+  }
+  return VIHMC_OK;
+}
+
+int dense_logp_grad(const vihmc_problem* p, long long C, const float* q, float* logp, float* grad, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  return dense_run(p, C, q, logp, grad, nullptr, ws, ws_bytes, st);
+}
+
+// forward only: MLP out[C,N]; DeepONet out[C,N,P] = Bout Tout^T + b0 written straight into `out`
+int dense_predict(const vihmc_problem* p, long long C, const float* q, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DensePlan pl;
+  if (int rc = make_plan(p, pl)) return rc;
+  if (!pl.deeponet) return dense_run(p, C, q, nullptr, nullptr, out, ws, ws_bytes, st);
+  if (p->act == VIHMC_ACT_SINE) return fail(VIHMC_ERR_UNSUPPORTED, "dense path implements tanh and relu");
+  if (ws == nullptr) return fail(VIHMC_ERR_WORKSPACE, "dense path needs a workspace");
+  const size_t shared_bytes = (size_t)pl.shared_floats * 4 + 2048;
+  if (ws_bytes <= shared_bytes) return fail(VIHMC_ERR_WORKSPACE, "workspace too small");
+  const long long cb_max = chains_per_batch(pl, C, ws_bytes - shared_bytes);
+  if (cb_max < 1) return fail(VIHMC_ERR_WORKSPACE, "workspace too small for one chain");
+  const long long D = pl.D, d = p->d, N = pl.N, P = pl.P;
+  Bump bump(static_cast<float*>(ws));
+  const float* trunk_in = p->x2;
+  if (p->impose_bc) {
+    float* feats = bump.take(P * 5);
+    trunk_features_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(p->x2, P, feats);
+    VIHMC_LAUNCH_OK("trunk_features_kernel");
+    trunk_in = feats;
+  }
+  float* batch_base = bump.take(0);
+  for (long long c0 = 0; c0 < C; c0 += cb_max) {
+    const int Cb = (int)((C - c0) < cb_max ? (C - c0) : cb_max);
+    Bump bb(batch_base);
+    float* Wf = bb.take((long long)Cb * D);
+    bb.take((long long)Cb * D);
+    float* acts_a[VIHMC_MAX_LAYERS];
+    float* acts_b[VIHMC_MAX_LAYERS];
+    for (int l = 0; l < pl.a.n_layers; ++l) acts_a[l] = bb.take((long long)Cb * N * pl.a.dims[l]);
+    for (int l = 0; l < pl.b.n_layers; ++l) acts_b[l] = bb.take((long long)Cb * P * pl.b.dims[l]);
+    float* part = bb.take(2LL * Cb * pl.head_tiles);
+    if (int rc = launch_scatter(p->frozen, reinterpret_cast<const long long*>(p->sens_ind), q + c0 * d, Wf, Cb, D, d, st)) return rc;
+    if (int rc = stack_forward(pl.a, p->x, N, Wf, D, acts_a, p->act, false, Cb, st)) return rc;
+    if (int rc = stack_forward(pl.b, trunk_in, P, Wf, D, acts_b, p->act, false, Cb, st)) return rc;
+    // O = Bout Tout^T + b0 through the HEAD epilogue with a zero target and prec = -1: C = -(-1) * (O - 0) = O
+    GemmArgs g{};
+    const int K = pl.K;
+    g.A = acts_a[pl.a.n_layers - 1]; g.a_bs = N * K; g.a_sm = K; g.a_sk = 1;
+    g.B = acts_b[pl.b.n_layers - 1]; g.b_bs = P * K; g.b_sk = 1; g.b_sn = K;
+    g.M = (int)N; g.N = (int)P; g.K = K;
+    g.C = out + c0 * N * P; g.c_bs = N * P; g.ldc = P;
+    g.bias = Wf; g.bias_bs = D;
+    g.part_ll = part; g.part_g = part + (long long)Cb * pl.head_tiles;
+    g.prec = -1.0f;
+    float* zero_row = bb.take(P);   // target row of zeros shared by every output row (ld_aux = 0)
+    VIHMC_CUDA_OK(cudaMemsetAsync(zero_row, 0, sizeof(float) * P, st));
+    g.aux = zero_row; g.aux_bs = 0; g.ld_aux = 0;
+    if (int rc = launch_gemm<EPI_HEAD>(g, Cb, st)) return rc;
+  }
+  return VIHMC_OK;
+}
+
 }  // namespace vihmc
