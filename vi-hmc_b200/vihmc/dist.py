@@ -1,0 +1,97 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), chains sharded, NO collective inside the leapfrog loop.
+
+The reference runs its chains one after another in a Python loop (main_VI_HMC.py:458-460), so chains are
+independent by construction: global chain ids [rank*C/G, (rank+1)*C/G) live on GPU `rank`, data and VI
+artefacts are replicated, and the Philox streams are keyed on the GLOBAL chain id so the draws do not
+depend on the sharding.  Collectives (NCCL on GPUs, gloo in the CPU tests) are used only AFTER sampling:
+gather of the stored draws and of per-half-chain moments for split-R-hat.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import diagnostics
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_chains(total_chains: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> Tuple[int, int]:
+    """(first global chain id, number of local chains) -- contiguous blocks, remainder spread over the low ranks."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    if total_chains < world_size:
+        raise ValueError(f"{total_chains} chains cannot be sharded over {world_size} ranks")
+    base, rem = divmod(total_chains, world_size)
+    n = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, n
+
+
+def gather_chains(local: torch.Tensor, total_chains: int, dst: int = 0, chain_dim: int = 1) -> Optional[torch.Tensor]:
+    """Gather [.., C_local, ..] shards (ragged allowed) to rank `dst` along `chain_dim`; other ranks get None."""
+    rank, w = world()
+    if w == 1:
+        return local
+    counts = [shard_chains(total_chains, r, w)[1] for r in range(w)]
+    moved = local.movedim(chain_dim, 0).contiguous()
+    cmax = max(counts)
+    if moved.shape[0] < cmax:  # pad ragged shards so every rank sends the same shape
+        pad = torch.zeros((cmax - moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+        moved = torch.cat([moved, pad], 0)
+    bufs = [torch.empty_like(moved) for _ in range(w)] if rank == dst else None
+    dist.gather(moved, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+    return out.movedim(0, chain_dim)
+
+
+def global_split_rhat(local_draws: torch.Tensor) -> torch.Tensor:
+    """Split-R-hat over ALL chains of all ranks from per-half-chain moments: each rank contributes
+    [2*C_local, d] means and variances (8*C_local*d bytes) instead of its draws.  Same value on every rank."""
+    mean, var, S = diagnostics.half_chain_moments(local_draws.reshape(local_draws.shape[0], local_draws.shape[1], -1))
+    rank, w = world()
+    if w > 1:
+        counts = torch.tensor([mean.shape[0]], device=mean.device)
+        all_counts = [torch.zeros_like(counts) for _ in range(w)]
+        dist.all_gather(all_counts, counts)
+        cmax = int(max(int(c) for c in all_counts))
+        def pad(t):
+            if t.shape[0] == cmax:
+                return t.contiguous()
+            return torch.cat([t, torch.zeros((cmax - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)], 0)
+        ms = [torch.empty((cmax,) + tuple(mean.shape[1:]), dtype=mean.dtype, device=mean.device) for _ in range(w)]
+        vs = [torch.empty_like(ms[0]) for _ in range(w)]
+        dist.all_gather(ms, pad(mean))
+        dist.all_gather(vs, pad(var))
+        mean = torch.cat([m[:int(c)] for m, c in zip(ms, all_counts)], 0)
+        var = torch.cat([v[:int(c)] for v, c in zip(vs, all_counts)], 0)
+    return diagnostics.rhat_from_moments(mean, var, S)
+
+
+def sample_sharded(specs, q0_all: torch.Tensor, total_chains: int, burn_in_draws: int = 0, gather: bool = True, **sampler_kw
+                   ) -> Dict[str, object]:
+    """Run the local shard of `total_chains` chains on this rank's GPU and gather on rank 0.
+
+    q0_all: [total_chains, d] start points (every rank passes the same tensor; each takes its rows).
+    burn_in_draws: stored rows to drop before the diagnostics (the caller-side `params_hmc[cfg.burn:]`).
+    Returns {'samples','logp','accepted' (rank 0: full; else None), 'rhat' (all ranks), 'local'}."""
+    from . import engine
+
+    chain0, n_local = shard_chains(total_chains)
+    res = engine.run_sampler(specs, q0_all[chain0:chain0 + n_local], chain_offset=chain0, to_host=False, **sampler_kw)
+    draws = res.samples[burn_in_draws:]
+    out = {"local": res, "rhat": global_split_rhat(draws) if draws.shape[0] >= 4 else None}
+    if gather:
+        out["samples"] = gather_chains(res.samples, total_chains)
+        out["logp"] = gather_chains(res.logp, total_chains) if res.logp is not None else None
+        out["accepted"] = gather_chains(res.accepted, total_chains) if res.accepted is not None else None
+    return out
