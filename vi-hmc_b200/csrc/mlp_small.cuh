@@ -4,18 +4,22 @@
 // reference closure (Neural_network/VI_HMC/main_VI_HMC.py:96-151 + my_make_func.py:52-73; call sites
 // main_VI_HMC.py:379-380 and Neural_network/HMC/main_regression_hmc.py:124-127).
 //
-// One gradient evaluation for one chain is 14 kFLOP + 400 tanh (1-10-10-1, N=20): far below any
-// UMMA tile, so this kernel runs on the FP32 pipes and is latency/issue bound, not HBM or tensor
-// bound.  Design:
-//   phase A  lane = data point: forward + backward through the net for that point in registers;
-//            weights are read from shared memory as warp-wide broadcasts (float4 rows);
-//            activations h and pre-activation gradients dz are written column-wise to shared memory.
-//   phase B  lane = sampled coordinate: g_i = sum_n dz[row_i][n] * h[col_i][n] (two float4 row reads
-//            per 4 data points) -- only the d sampled coordinates are ever reduced (VI-HMC subset);
-//            the prior gradient and the leapfrog kick/drift are fused into the same pass, which also
-//            scatters the new q_i into the full weight table (the VI-HMC masked update).
-//   The whole num_samples x (L+1) loop, Philox momenta, both Hamiltonians, the Metropolis test and
-//   hamiltorch's storage rule run inside ONE launch; the only HBM traffic is the stored samples.
+// One gradient evaluation for one chain is 14 kFLOP + 400 tanh (1-10-10-1, N=20): far below any UMMA
+// tile and with per-chain weights, so this kernel runs on the FP32 pipes and is latency / issue bound,
+// not HBM or tensor bound.  v2 mapping (v1 = lane per data point measured 6.9 cycles per instruction,
+// dominated by dependent-FMA waits and instruction-cache misses of fully unrolled code):
+//   unit mode   lane = (hidden unit j, point group g), G = 32 / W groups, 8 data points per lane.
+//               A lane keeps its weight row in registers and accumulates 8 independent dot products
+//               (ILP 8 hides FMA / MUFU / shared-memory latency inside one warp); inputs are float4
+//               reads of [unit][point] rows that all lanes of a group share (broadcast).  The layer
+//               loop is a runtime loop, so the whole evaluation is a few hundred instructions of
+//               re-used code.  The backward data pass is the same routine on a transposed weight table.
+//   point mode  lane = data point: output layer, residual, likelihood.
+//   phase B     lane = sampled coordinate: g_i = sum_n dz[row_i][n] * h[col_i][n] over float4 rows --
+//               only the d sampled coordinates are reduced (VI-HMC subset); prior gradient, kick, drift
+//               and the scatter of the new q_i into both weight tables are fused into the same pass.
+//   The whole num_samples x (L+1) loop, Philox momenta, both Hamiltonians, the Metropolis test,
+//   hamiltorch's storage rule and dual averaging run inside ONE launch; HBM sees only the samples.
 #pragma once
 #include "common.cuh"
 
@@ -24,14 +28,15 @@ namespace vihmc {
 constexpr int kMaxHidden = 4;
 
 struct SmallLayout {
-  // weight region (floats from the chain base)
-  int wbase[kMaxHidden + 1], ws[kMaxHidden + 1], bbase[kMaxHidden + 1];
+  // weight region (floats from the chain base): row-major [unit][row stride] tables, and for the
+  // hidden->hidden layers a transposed copy [input unit][WSW] used by the backward data pass
+  int wbase[kMaxHidden + 1], ws[kMaxHidden + 1], bbase[kMaxHidden + 1], tbase[kMaxHidden + 1];
   int w_total;
-  // per-coordinate state, each dp floats/ints
-  int q, p, g, qf, pmu, piv, meta, wpos;
-  // activation region
-  int act_base, xs, h, dz, dO, ones;
-  int NC, dp, total;
+  // per-coordinate state, each dp entries
+  int q, p, g, qf, pmu, piv, meta, wpos, wposT;
+  // activation region: rows of NCS floats
+  int act_base, xs, h, da, dz, dO, ones;
+  int NC, NCS, dp, total;
 };
 
 struct SmallParams {
@@ -47,7 +52,7 @@ struct SmallParams {
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // W = padded hidden width the kernel is compiled for
-inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, long long N) {
+inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, long long /*N*/) {
   SmallLayout L{};
   const int WSW = round_up(W, 4);
   int off = 0;
@@ -58,6 +63,8 @@ inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, lon
     off += rows * L.ws[l];
     L.bbase[l] = off;
     off += l < n_hidden ? WSW : 4;
+    L.tbase[l] = off;
+    if (l >= 1 && l < n_hidden) off += W * WSW;
   }
   L.w_total = off;
   L.dp = round_up((int)d, 4);
@@ -69,33 +76,39 @@ inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, lon
   L.piv = off; off += L.dp;
   L.meta = off; off += L.dp;
   L.wpos = off; off += L.dp;
-  L.NC = N >= 32 ? 32 : round_up((int)N, 4);
+  L.wposT = off; off += L.dp;
+  L.NC = (32 / W) * 8;
+  L.NCS = L.NC + 4;   // +4: eight different rows land in eight different bank groups
   L.act_base = off;
   int a = 0;
-  L.xs = a; a += in_dim * L.NC;
-  L.h = a; a += n_hidden * W * L.NC;
-  L.dz = a; a += n_hidden * W * L.NC;
-  L.dO = a; a += L.NC;
-  L.ones = a; a += L.NC;
+  L.xs = a; a += in_dim * L.NCS;
+  L.h = a; a += n_hidden * W * L.NCS;
+  L.da = a; a += n_hidden * W * L.NCS;
+  L.dz = a; a += n_hidden * W * L.NCS;
+  L.dO = a; a += L.NCS;
+  L.ones = a; a += L.NCS;
   L.total = off + a;
   return L;
 }
 
-// full flat index f -> (position in the padded weight table, phase-B row offsets)
-__device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long long f, int& wpos, int& a_off, int& b_off) {
+// full flat index f -> positions in the weight tables and the phase-B row offsets
+__device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long long f, int& wpos, int& wposT, int& a_off,
+                                             int& b_off) {
   const SmallLayout& L = P.lay;
+  const int WSW = (W + 3) / 4 * 4;
   long long base = 0;
-  wpos = 0; a_off = L.dO; b_off = L.ones;
+  wpos = 0; wposT = -1; a_off = L.dO; b_off = L.ones;
   for (int l = 0; l <= P.n_hidden; ++l) {
     const int out_l = l < P.n_hidden ? P.widths[l] : 1;
     const int in_l = l == 0 ? P.in_dim : P.widths[l - 1];
-    const int arow = l < P.n_hidden ? L.dz + l * W * L.NC : L.dO;
+    const int arow = l < P.n_hidden ? L.dz + l * W * L.NCS : L.dO;
     const long long numel = (long long)out_l * in_l;
     if (f < base + numel) {
       const int j = (int)((f - base) / in_l), k = (int)((f - base) % in_l);
       wpos = L.wbase[l] + j * L.ws[l] + k;
-      a_off = arow + (l < P.n_hidden ? j * L.NC : 0);
-      b_off = l == 0 ? L.xs + k * L.NC : L.h + ((l - 1) * W + k) * L.NC;
+      if (l >= 1 && l < P.n_hidden) wposT = L.tbase[l] + k * WSW + j;
+      a_off = arow + (l < P.n_hidden ? j * L.NCS : 0);
+      b_off = l == 0 ? L.xs + k * L.NCS : L.h + ((l - 1) * W + k) * L.NCS;
       return;
     }
     base += numel;
@@ -103,7 +116,7 @@ __device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long l
       if (f < base + out_l) {
         const int j = (int)(f - base);
         wpos = L.bbase[l] + j;
-        a_off = arow + (l < P.n_hidden ? j * L.NC : 0);
+        a_off = arow + (l < P.n_hidden ? j * L.NCS : 0);
         b_off = L.ones;
         return;
       }
@@ -112,31 +125,118 @@ __device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long l
   }
 }
 
-// One-time per-chain setup: zero the padded weight table, load frozen weights, decode coordinates,
-// load the prior, load q (and scatter it into the weight table).
+// tanh with tanhf-class accuracy and no divergent branch: |x| < 0.55 minimax odd polynomial (fp32 max
+// rel. error 6.5e-8), otherwise 1 - 2/(exp(2|x|)+1) on ex2.approx / rcp.approx (<= 1.8e-7).
+__device__ __forceinline__ float tanh_sel(float x) {
+  const float ax = fabsf(x), x2 = x * x;
+  float p = -6.6157488502e-03f;
+  p = fmaf(p, x2, 2.1312740519e-02f);
+  p = fmaf(p, x2, -5.3910065611e-02f);
+  p = fmaf(p, x2, 1.3333117609e-01f);
+  p = fmaf(p, x2, -3.3333332045e-01f);
+  const float small = fmaf(x * x2, p, x);
+  const float e = __expf(2.0f * ax);
+  const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+  return ax < 0.55f ? small : big;
+}
+
+// in: z[8] pre-activations; out: z[8] = act(z), da[8] = act'(z)
+__device__ __forceinline__ void activate8(int act, float (&z)[8], float (&da)[8]) {
+  if (act == VIHMC_ACT_TANH) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      z[t] = tanh_sel(z[t]);
+      da[t] = fmaf(-z[t], z[t], 1.0f);
+    }
+  } else if (act == VIHMC_ACT_RELU) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      da[t] = z[t] > 0.0f ? 1.0f : 0.0f;
+      z[t] = z[t] > 0.0f ? z[t] : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float s, c;
+      sincosf(z[t], &s, &c);
+      z[t] = s;
+      da[t] = c;
+    }
+  }
+}
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// acc[t] += sum_k wrow[k] * rows[k][t], t < 8: the weight row sits in registers, 8 independent chains
+template <int W, int NCS>
+__device__ __forceinline__ void dot_rows(const float* wrow, const float* rows, float (&acc)[8]) {
+  constexpr int WSW = (W + 3) / 4 * 4;
+  float w[WSW];
+#pragma unroll
+  for (int k4 = 0; k4 < WSW / 4; ++k4) {
+    const float4 v = reinterpret_cast<const float4*>(wrow)[k4];
+    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    float r[8];
+    load8(rows + k * NCS, r);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = fmaf(w[k], r[t], acc[t]);
+  }
+}
+
+// point-mode staging of one data chunk: x columns, validity row; returns this lane's target
 template <int W>
-__device__ void chain_init(float* sm, const SmallParams& P, const float* q_row, int lane) {
+__device__ __forceinline__ float stage_chunk(float* sm, const SmallParams& P, int lane, int chunk) {
+  constexpr int NC = (32 / W) * 8, NCS = NC + 4;
+  const SmallLayout& L = P.lay;
+  float* act = sm + L.act_base;
+  float yv = 0.0f;
+  if (lane < NC) {
+    const long long n = (long long)chunk * NC + lane;
+    const bool valid = n < P.N;
+    for (int k = 0; k < P.in_dim; ++k) act[L.xs + k * NCS + lane] = valid ? __ldg(P.x + n * P.in_dim + k) : 0.0f;
+    act[L.ones + lane] = valid ? 1.0f : 0.0f;
+    yv = valid ? __ldg(P.y + n) : 0.0f;
+  }
+  return yv;
+}
+
+// One-time per-chain setup: zero the weight tables, load frozen weights, decode coordinates, load
+// the prior and q (scattered into the tables).  Returns this lane's target when N fits one chunk.
+template <int W>
+__device__ float chain_init(float* sm, const SmallParams& P, const float* q_row, int lane) {
   const SmallLayout& L = P.lay;
   for (int i = lane; i < L.act_base; i += 32) sm[i] = 0.0f;
-  float* act = sm + L.act_base;
-  for (int i = lane; i < L.NC; i += 32) act[L.ones + i] = 0.0f;
   __syncwarp();
   if (P.frozen != nullptr) {
     for (long long f = lane; f < P.D; f += 32) {
-      int wpos, a, b;
-      decode_coord(P, W, f, wpos, a, b);
-      sm[wpos] = __ldg(P.frozen + f);
+      int wpos, wposT, a, b;
+      decode_coord(P, W, f, wpos, wposT, a, b);
+      const float v = __ldg(P.frozen + f);
+      sm[wpos] = v;
+      if (wposT >= 0) sm[wposT] = v;
     }
   }
   __syncwarp();
   int* meta = reinterpret_cast<int*>(sm + L.meta);
   int* wposv = reinterpret_cast<int*>(sm + L.wpos);
+  int* wposTv = reinterpret_cast<int*>(sm + L.wposT);
   for (int i = lane; i < (int)P.d; i += 32) {
     const long long f = P.sens_ind ? __ldg(P.sens_ind + i) : (long long)i;
-    int wpos, a, b;
-    decode_coord(P, W, f, wpos, a, b);
+    int wpos, wposT, a, b;
+    decode_coord(P, W, f, wpos, wposT, a, b);
     meta[i] = (a << 16) | b;
     wposv[i] = wpos;
+    wposTv[i] = wposT;
     const float sig = P.prior_sigma ? __ldg(P.prior_sigma + i) : P.prior_sigma_scalar;
     sm[L.piv + i] = isinf(sig) ? 0.0f : 1.0f / (sig * sig);
     sm[L.pmu + i] = P.prior_mu ? __ldg(P.prior_mu + i) : 0.0f;
@@ -144,211 +244,199 @@ __device__ void chain_init(float* sm, const SmallParams& P, const float* q_row, 
     sm[L.q + i] = qv;
     sm[L.qf + i] = qv;
     sm[wpos] = qv;
+    if (wposT >= 0) sm[wposT] = qv;
   }
+  const float yv = stage_chunk<W>(sm, P, lane, 0);
   __syncwarp();
+  return yv;
 }
 
-// Phase A + phase B over all data chunks.  On return sm[g + i] holds d loglik / d q_i (no prior yet)
-// and the return value is this lane's share of the log-likelihood (to be warp-summed by the caller).
-template <int W, int NH>
-__device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallParams& P, const Likelihood lik, int lane) {
+// forward pass of the staged chunk; returns the network output of this lane's data point (point mode)
+template <int W>
+__device__ __forceinline__ float forward_chunk(float* sm, const SmallParams& P, int lane) {
+  constexpr int G = 32 / W, NC = G * 8, NCS = NC + 4, WSW = (W + 3) / 4 * 4;
   const SmallLayout& L = P.lay;
-  constexpr int WSW = (W + 3) / 4 * 4;
   float* act = sm + L.act_base;
-  const int NC = L.NC;
-  float ll_lane = 0.0f;
-  const int n_chunks = (int)((P.N + 31) / 32);
-  for (int chunk = 0; chunk < n_chunks; ++chunk) {
-    const long long n = (long long)chunk * 32 + lane;
-    const bool valid = n < P.N && lane < NC;
-    // ---------------- phase A: lane = data point ----------------
-    if (lane < NC) {
-      for (int k = 0; k < P.in_dim; ++k) act[L.xs + k * NC + lane] = valid ? __ldg(P.x + n * P.in_dim + k) : 0.0f;
-      act[L.ones + lane] = valid ? 1.0f : 0.0f;
-      const float yv = valid ? __ldg(P.y + n) : 0.0f;
-      float h[W], da[NH][W];
-      // layer 0 (runtime input width)
-      {
-        const float* w0 = sm + L.wbase[0];
-        const float* b0 = sm + L.bbase[0];
-        const int ws0 = L.ws[0];
+  const int j = lane % W, c0 = (lane / W) * 8;
+  const bool unit = lane < G * W;
+  if (unit) {  // layer 0: runtime input width
+    float z[8], da[8];
+    const float b = sm[L.bbase[0] + j];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          float z = b0[j];
-          for (int k = 0; k < P.in_dim; ++k) z = fmaf(w0[j * ws0 + k], act[L.xs + k * NC + lane], z);
-          h[j] = act_fwd(P.act, z, da[0][j]);
-          act[L.h + j * NC + lane] = h[j];
-        }
-      }
-      // hidden layers 1..NH-1
+    for (int t = 0; t < 8; ++t) z[t] = b;
+    for (int k = 0; k < P.in_dim; ++k) {
+      const float w = sm[L.wbase[0] + j * L.ws[0] + k];
+      float r[8];
+      load8(act + L.xs + k * NCS + c0, r);
 #pragma unroll
-      for (int l = 1; l < NH; ++l) {
-        const float* wl = sm + L.wbase[l];
-        const float* bl = sm + L.bbase[l];
-        float hn[W];
+      for (int t = 0; t < 8; ++t) z[t] = fmaf(w, r[t], z[t]);
+    }
+    activate8(P.act, z, da);
+    store8(act + L.h + j * NCS + c0, z);
+    store8(act + L.da + j * NCS + c0, da);
+  }
+  __syncwarp();
+  for (int l = 1; l < P.n_hidden; ++l) {
+    if (unit) {
+      float z[8], da[8];
+      const float b = sm[L.bbase[l] + j];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          const float4* row = reinterpret_cast<const float4*>(wl + j * WSW);
-          float z = bl[j];
-#pragma unroll
-          for (int k4 = 0; k4 < WSW / 4; ++k4) {
-            const float4 w = row[k4];
-            if (4 * k4 + 0 < W) z = fmaf(w.x, h[4 * k4 + 0], z);
-            if (4 * k4 + 1 < W) z = fmaf(w.y, h[4 * k4 + 1], z);
-            if (4 * k4 + 2 < W) z = fmaf(w.z, h[4 * k4 + 2], z);
-            if (4 * k4 + 3 < W) z = fmaf(w.w, h[4 * k4 + 3], z);
-          }
-          hn[j] = act_fwd(P.act, z, da[l][j]);
-          act[L.h + (l * W + j) * NC + lane] = hn[j];
-        }
-#pragma unroll
-        for (int j = 0; j < W; ++j) h[j] = hn[j];
-      }
-      // output layer (out_dim = 1) + Gaussian likelihood
-      const float* wo = sm + L.wbase[NH];
-      float o = sm[L.bbase[NH]];
-      float wov[W];
-#pragma unroll
-      for (int k4 = 0; k4 < WSW / 4; ++k4) {
-        const float4 w = reinterpret_cast<const float4*>(wo)[k4];
-        if (4 * k4 + 0 < W) wov[4 * k4 + 0] = w.x;
-        if (4 * k4 + 1 < W) wov[4 * k4 + 1] = w.y;
-        if (4 * k4 + 2 < W) wov[4 * k4 + 2] = w.z;
-        if (4 * k4 + 3 < W) wov[4 * k4 + 3] = w.w;
-      }
-#pragma unroll
-      for (int k = 0; k < W; ++k) o = fmaf(wov[k], h[k], o);
-      const float r = o - yv;
-      const float dO = valid ? -lik.prec * r : 0.0f;
-      if (valid) ll_lane += lik.ll_const - lik.half_prec * r * r;
-      act[L.dO + lane] = dO;
-      // backward
-      float dh[W];
-#pragma unroll
-      for (int k = 0; k < W; ++k) dh[k] = wov[k] * dO;
-#pragma unroll
-      for (int l = NH - 1; l >= 0; --l) {
-        float dz[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-          dz[j] = dh[j] * da[l][j];
-          act[L.dz + (l * W + j) * NC + lane] = dz[j];
-        }
-        if (l > 0) {
-          const float* wl = sm + L.wbase[l];
-#pragma unroll
-          for (int k = 0; k < W; ++k) dh[k] = 0.0f;
-#pragma unroll
-          for (int j = 0; j < W; ++j) {
-            const float4* row = reinterpret_cast<const float4*>(wl + j * WSW);
-#pragma unroll
-            for (int k4 = 0; k4 < WSW / 4; ++k4) {
-              const float4 w = row[k4];
-              if (4 * k4 + 0 < W) dh[4 * k4 + 0] = fmaf(w.x, dz[j], dh[4 * k4 + 0]);
-              if (4 * k4 + 1 < W) dh[4 * k4 + 1] = fmaf(w.y, dz[j], dh[4 * k4 + 1]);
-              if (4 * k4 + 2 < W) dh[4 * k4 + 2] = fmaf(w.z, dz[j], dh[4 * k4 + 2]);
-              if (4 * k4 + 3 < W) dh[4 * k4 + 3] = fmaf(w.w, dz[j], dh[4 * k4 + 3]);
-            }
-          }
-        }
-      }
+      for (int t = 0; t < 8; ++t) z[t] = b;
+      dot_rows<W, NCS>(sm + L.wbase[l] + j * WSW, act + L.h + (l - 1) * W * NCS + c0, z);
+      activate8(P.act, z, da);
+      store8(act + L.h + (l * W + j) * NCS + c0, z);
+      store8(act + L.da + (l * W + j) * NCS + c0, da);
     }
     __syncwarp();
-    // ---------------- phase B: lane = sampled coordinate ----------------
-    const int* meta = reinterpret_cast<const int*>(sm + L.meta);
-    for (int i = lane; i < (int)P.d; i += 32) {
-      const int m = meta[i];
-      const float4* A = reinterpret_cast<const float4*>(act + (m >> 16));
-      const float4* B = reinterpret_cast<const float4*>(act + (m & 0xffff));
-      float acc0 = 0.0f, acc1 = 0.0f;
-      for (int c = 0; c < NC / 4; ++c) {
-        const float4 a = A[c], b = B[c];
-        acc0 = fmaf(a.x, b.x, acc0);
-        acc1 = fmaf(a.y, b.y, acc1);
-        acc0 = fmaf(a.z, b.z, acc0);
-        acc1 = fmaf(a.w, b.w, acc1);
-      }
-      const float gsum = acc0 + acc1;
-      sm[L.g + i] = chunk == 0 ? gsum : sm[L.g + i] + gsum;
+  }
+  float o = 0.0f;
+  if (lane < NC) {  // output layer, out_dim = 1
+    const float* wo = sm + L.wbase[P.n_hidden];
+    const float* hl = act + L.h + (P.n_hidden - 1) * W * NCS + lane;
+    o = sm[L.bbase[P.n_hidden]];
+#pragma unroll
+    for (int k = 0; k < W; ++k) o = fmaf(wo[k], hl[k * NCS], o);
+  }
+  return o;
+}
+
+// backward pass: writes the pre-activation gradients dz of every hidden layer (dO is already in smem)
+template <int W>
+__device__ __forceinline__ void backward_chunk(float* sm, const SmallParams& P, int lane) {
+  constexpr int G = 32 / W, NC = G * 8, NCS = NC + 4, WSW = (W + 3) / 4 * 4;
+  const SmallLayout& L = P.lay;
+  float* act = sm + L.act_base;
+  const int j = lane % W, c0 = (lane / W) * 8;
+  const bool unit = lane < G * W;
+  const int top = P.n_hidden - 1;
+  if (unit) {
+    float dO[8], da[8], dz[8];
+    const float wo = sm[L.wbase[P.n_hidden] + j];
+    load8(act + L.dO + c0, dO);
+    load8(act + L.da + (top * W + j) * NCS + c0, da);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dz[t] = wo * dO[t] * da[t];
+    store8(act + L.dz + (top * W + j) * NCS + c0, dz);
+  }
+  __syncwarp();
+  for (int l = top; l >= 1; --l) {
+    if (unit) {
+      float acc[8], da[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
+      dot_rows<W, NCS>(sm + L.tbase[l] + j * WSW, act + L.dz + l * W * NCS + c0, acc);
+      load8(act + L.da + ((l - 1) * W + j) * NCS + c0, da);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] *= da[t];
+      store8(act + L.dz + ((l - 1) * W + j) * NCS + c0, acc);
     }
+    __syncwarp();
+  }
+}
+
+// phase B: lane = sampled coordinate; accumulates d loglik / d q_i of the staged chunk into sm[g]
+template <int W>
+__device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int lane, bool first_chunk) {
+  constexpr int NC = (32 / W) * 8;
+  const SmallLayout& L = P.lay;
+  const float* act = sm + L.act_base;
+  const int* meta = reinterpret_cast<const int*>(sm + L.meta);
+  for (int i = lane; i < (int)P.d; i += 32) {
+    const int m = meta[i];
+    const float4* A = reinterpret_cast<const float4*>(act + (m >> 16));
+    const float4* B = reinterpret_cast<const float4*>(act + (m & 0xffff));
+    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NC / 4; ++c) {
+      const float4 a = A[c], b = B[c];
+      acc0 = fmaf(a.x, b.x, acc0);
+      acc1 = fmaf(a.y, b.y, acc1);
+      acc2 = fmaf(a.z, b.z, acc2);
+      acc3 = fmaf(a.w, b.w, acc3);
+    }
+    const float gsum = (acc0 + acc1) + (acc2 + acc3);
+    sm[L.g + i] = first_chunk ? gsum : sm[L.g + i] + gsum;
+  }
+}
+
+// Likelihood gradient w.r.t. every sampled coordinate into sm[g] (no prior yet); returns this lane's
+// share of the log-likelihood.  yv0 = the lane's target when the data fit one chunk.
+template <int W>
+__device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallParams& P, const Likelihood lik, int lane, float yv0) {
+  constexpr int NC = (32 / W) * 8;
+  const SmallLayout& L = P.lay;
+  float* act = sm + L.act_base;
+  const int n_chunks = (int)((P.N + NC - 1) / NC);
+  float ll_lane = 0.0f;
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    float yv = yv0;
+    if (n_chunks > 1) {
+      yv = stage_chunk<W>(sm, P, lane, chunk);
+      __syncwarp();
+    }
+    const float o = forward_chunk<W>(sm, P, lane);
+    if (lane < NC) {
+      const bool valid = (long long)chunk * NC + lane < P.N;
+      const float r = o - yv;
+      act[L.dO + lane] = valid ? -lik.prec * r : 0.0f;
+      if (valid) ll_lane += lik.ll_const - lik.half_prec * r * r;
+    }
+    __syncwarp();
+    backward_chunk<W>(sm, P, lane);
+    phase_b<W>(sm, P, lane, chunk == 0);
     __syncwarp();
   }
   return ll_lane;
 }
 
-// Adds the prior to sm[g] and returns this lane's share of sum_i -0.5 (q-mu)^2 / sigma^2.
-__device__ __forceinline__ float add_prior(float* sm, const SmallParams& P, int lane) {
-  const SmallLayout& L = P.lay;
-  float lp = 0.0f;
-  for (int i = lane; i < (int)P.d; i += 32) {
-    const float dq = sm[L.q + i] - sm[L.pmu + i], iv = sm[L.piv + i];
-    lp = fmaf(-0.5f * dq * dq, iv, lp);
-    sm[L.g + i] = fmaf(-dq * iv, P.inv_prior_scale, sm[L.g + i]);
-  }
-  return lp;
-}
-
 // ------------------------------------------------------------------------------------------------
 // kernel 1: log-posterior value + gradient for C chains (vihmc_logp_grad, MLP small path)
 // ------------------------------------------------------------------------------------------------
-template <int W, int NH>
+template <int W>
 __global__ void __launch_bounds__(128) mlp_small_logp_grad_kernel(SmallParams P, long long C, const float* __restrict__ q,
                                                                   float* __restrict__ logp, float* __restrict__ grad) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long chain = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (chain >= C) return;
-  float* sm = smem + (size_t)warp * P.lay.total;
-  chain_init<W>(sm, P, q + chain * P.d, lane);
+  const SmallLayout& L = P.lay;
+  float* sm = smem + (size_t)warp * L.total;
+  const float yv0 = chain_init<W>(sm, P, q + chain * P.d, lane);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
-  const float ll_lane = eval_likelihood_grad<W, NH>(sm, P, lik, lane);
-  const float lp_lane = add_prior(sm, P, lane);
-  __syncwarp();
+  const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0);
+  float lp_lane = 0.0f;
+  for (int i = lane; i < (int)P.d; i += 32) {
+    const float dq = sm[L.q + i] - sm[L.pmu + i], iv = sm[L.piv + i];
+    lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
+    if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, sm[L.g + i]);
+  }
   const float total = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + P.prior_log_norm * P.inv_prior_scale;
   if (lane == 0) logp[chain] = total;
-  if (grad != nullptr)
-    for (int i = lane; i < (int)P.d; i += 32) grad[chain * P.d + i] = sm[P.lay.g + i];
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel 1b: forward only (vihmc_predict, MLP small path): out[C, N]
 // ------------------------------------------------------------------------------------------------
-template <int W, int NH>
+template <int W>
 __global__ void __launch_bounds__(128) mlp_small_predict_kernel(SmallParams P, long long C, const float* __restrict__ q,
                                                                 float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int NC = (32 / W) * 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long chain = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (chain >= C) return;
   float* sm = smem + (size_t)warp * P.lay.total;
   chain_init<W>(sm, P, q + chain * P.d, lane);
-  const SmallLayout& L = P.lay;
-  constexpr int WSW = (W + 3) / 4 * 4;
-  for (long long n = lane; n < P.N; n += 32) {
-    float h[W], dummy;
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-      float z = sm[L.bbase[0] + j];
-      for (int k = 0; k < P.in_dim; ++k) z = fmaf(sm[L.wbase[0] + j * L.ws[0] + k], __ldg(P.x + n * P.in_dim + k), z);
-      h[j] = act_fwd(P.act, z, dummy);
+  const int n_chunks = (int)((P.N + NC - 1) / NC);
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    if (chunk > 0) {
+      stage_chunk<W>(sm, P, lane, chunk);
+      __syncwarp();
     }
-#pragma unroll
-    for (int l = 1; l < NH; ++l) {
-      float hn[W];
-#pragma unroll
-      for (int j = 0; j < W; ++j) {
-        float z = sm[L.bbase[l] + j];
-#pragma unroll
-        for (int k = 0; k < W; ++k) z = fmaf(sm[L.wbase[l] + j * WSW + k], h[k], z);
-        hn[j] = act_fwd(P.act, z, dummy);
-      }
-#pragma unroll
-      for (int j = 0; j < W; ++j) h[j] = hn[j];
-    }
-    float o = sm[L.bbase[NH]];
-#pragma unroll
-    for (int k = 0; k < W; ++k) o = fmaf(sm[L.wbase[NH] + k], h[k], o);
-    out[chain * P.N + n] = o;
+    const float o = forward_chunk<W>(sm, P, lane);
+    const long long n = (long long)chunk * NC + lane;
+    if (lane < NC && n < P.N) out[chain * P.N + n] = o;
+    __syncwarp();
   }
 }
 
@@ -368,7 +456,7 @@ struct SampleArgs {
   const float* inj_u;
 };
 
-template <int W, int NH>
+template <int W>
 __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -379,8 +467,9 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
   const int d = (int)P.d;
   const long long C = A.C;
   const float* q0 = A.q0 + chain * d;
-  chain_init<W>(sm, P, q0, lane);
+  const float yv0 = chain_init<W>(sm, P, q0, lane);
   const int* wposv = reinterpret_cast<const int*>(sm + L.wpos);
+  const int* wposTv = reinterpret_cast<const int*>(sm + L.wposT);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
   const unsigned long long gchain = (unsigned long long)(A.cfg.chain_offset + chain);
   const int S = A.cfg.num_samples, nsteps = A.cfg.num_steps, burn = A.cfg.burn;
@@ -391,8 +480,7 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
   const float eps_init = A.cfg.step_size;
   float eps_bar = 1.0f, H_t = 0.0f;
 
-  // stored row 0 = params_init
-  for (int i = lane; i < d; i += 32) A.samples[chain * d + i] = sm[L.q + i];
+  for (int i = lane; i < d; i += 32) A.samples[chain * d + i] = sm[L.q + i];  // stored row 0 = params_init
   float logp_init = 0.0f, logp_f = 0.0f;  // log-posterior of params_init / of the fallback state
 
   for (int n = 0; n < S; ++n) {
@@ -410,74 +498,60 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
         ke = fmaf(pv, pv, ke);
       }
     } else {
-      for (int j = lane; 4 * j < d; j += 32) {
-        const float4 z = philox_normal4(A.cfg.seed, gchain, (uint32_t)n, (uint32_t)j, STREAM_MOMENTUM);
+      for (int jb = lane; 4 * jb < d; jb += 32) {
+        const float4 z = philox_normal4(A.cfg.seed, gchain, (uint32_t)n, (uint32_t)jb, STREAM_MOMENTUM);
         const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          if (4 * j + t < d) {
-            sm[L.p + 4 * j + t] = zz[t];
+          if (4 * jb + t < d) {
+            sm[L.p + 4 * jb + t] = zz[t];
             ke = fmaf(zz[t], zz[t], ke);
           }
       }
     }
+    const float ke0 = 0.5f * warp_sum(ke);
     __syncwarp();
-    // ---- H0 and first half kick + first drift ----
-    float ll_lane = eval_likelihood_grad<W, NH>(sm, P, lik, lane);
-    float lp_lane = add_prior(sm, P, lane);
-    __syncwarp();
-    const float logp0 = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + log_norm;
-    const float H0 = -logp0 + 0.5f * warp_sum(ke);
+
+    // ---- trajectory: evaluation s = 0 yields H0 and the first half kick; s = nsteps yields H1 ----
+    const float half_eps = 0.5f * eps;
+    float logp0 = 0.0f, logp1 = 0.0f, ke1 = 0.0f;
+    for (int s = 0; s <= nsteps; ++s) {
+      const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0);
+      const bool first = s == 0, last = s == nsteps;
+      const float kick = first ? half_eps : eps;
+      float lp_lane = 0.0f, ke_lane = 0.0f;
+      for (int i = lane; i < d; i += 32) {
+        const float qv0 = sm[L.q + i];
+        const float dq = qv0 - sm[L.pmu + i], iv = sm[L.piv + i];
+        lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
+        const float gi = fmaf(-dq * iv, P.inv_prior_scale, sm[L.g + i]);
+        float pv = axpy_unfused(kick, gi, sm[L.p + i]);
+        if (last) {
+          // hamiltorch: p += eps*g inside the loop, then ret_momenta[-1] - 0.5*eps*g (separately rounded)
+          pv = __fsub_rn(pv, __fmul_rn(half_eps, gi));
+          ke_lane = fmaf(pv, pv, ke_lane);
+        } else {
+          const float qv = axpy_unfused(eps, pv, qv0);
+          sm[L.q + i] = qv;
+          sm[wposv[i]] = qv;
+          const int wt = wposTv[i];
+          if (wt >= 0) sm[wt] = qv;
+        }
+        sm[L.p + i] = pv;
+      }
+      if (first || last) {
+        const float lp = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + log_norm;
+        if (first) logp0 = lp;
+        if (last) { logp1 = lp; ke1 = 0.5f * warp_sum(ke_lane); }
+      }
+      __syncwarp();
+    }
+    const float H0 = -logp0 + ke0, H1 = -logp1 + ke1;
     if (n == 0) {
       logp_init = logp0;
       logp_f = logp0;
       if (A.logp_out != nullptr && lane == 0) A.logp_out[chain] = logp0;
     }
-    const float half_eps = 0.5f * eps;
-    for (int i = lane; i < d; i += 32) {
-      const float pv = axpy_unfused(half_eps, sm[L.g + i], sm[L.p + i]);
-      const float qv = axpy_unfused(eps, pv, sm[L.q + i]);
-      sm[L.p + i] = pv;
-      sm[L.q + i] = qv;
-      sm[wposv[i]] = qv;
-    }
-    __syncwarp();
-    // ---- L leapfrog steps ----
-    float logp1 = 0.0f, ke1 = 0.0f;
-    for (int s = 1; s <= nsteps; ++s) {
-      ll_lane = eval_likelihood_grad<W, NH>(sm, P, lik, lane);
-      if (s < nsteps) {
-        for (int i = lane; i < d; i += 32) {
-          const float dq = sm[L.q + i] - sm[L.pmu + i];
-          const float gi = fmaf(-dq * sm[L.piv + i], P.inv_prior_scale, sm[L.g + i]);
-          const float pv = axpy_unfused(eps, gi, sm[L.p + i]);
-          const float qv = axpy_unfused(eps, pv, sm[L.q + i]);
-          sm[L.p + i] = pv;
-          sm[L.q + i] = qv;
-          sm[wposv[i]] = qv;
-        }
-      } else {
-        lp_lane = 0.0f;
-        for (int i = lane; i < d; i += 32) {
-          const float dq = sm[L.q + i] - sm[L.pmu + i], iv = sm[L.piv + i];
-          lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
-          const float gi = fmaf(-dq * iv, P.inv_prior_scale, sm[L.g + i]);
-          float pv = axpy_unfused(eps, gi, sm[L.p + i]);
-          pv = __fsub_rn(pv, __fmul_rn(half_eps, gi));
-          sm[L.p + i] = pv;
-          ke1 = fmaf(pv, pv, ke1);
-        }
-        logp1 = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + log_norm;
-        ke1 = 0.5f * warp_sum(ke1);
-      }
-      __syncwarp();
-    }
-    if (nsteps == 0) {  // degenerate: proposal == current state, p = p + eps/2 g - eps/2 g
-      logp1 = logp0;
-      for (int i = lane; i < d; i += 32) ke1 = fmaf(sm[L.p + i], sm[L.p + i], ke1);
-      ke1 = 0.5f * warp_sum(ke1);
-    }
-    const float H1 = -logp1 + ke1;
     // ---- Metropolis test (hamiltorch: rho = min(0, H0-H1); accept iff rho >= log u) ----
     const float u = A.inj_u != nullptr ? A.inj_u[(long long)n * C + chain] : philox_uniform(A.cfg.seed, gchain, (uint32_t)n);
     const float rho = fminf(0.0f, H0 - H1);
@@ -497,6 +571,8 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
         const float qv = sm[L.qf + i];
         sm[L.q + i] = qv;
         sm[wposv[i]] = qv;
+        const int wt = wposTv[i];
+        if (wt >= 0) sm[wt] = qv;
         if (store) row[i] = qv;
       }
     }
@@ -527,7 +603,9 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
   if (A.step_sizes != nullptr && lane == 0) A.step_sizes[chain] = eps;
 }
 
-
+// ------------------------------------------------------------------------------------------------
+// launch helpers shared by the per-width translation units
+// ------------------------------------------------------------------------------------------------
 enum SmallOp { kOpLogpGrad = 0, kOpPredict = 1, kOpSample = 2 };
 
 struct SmallLaunch {
@@ -547,37 +625,26 @@ static int set_smem(K kernel, size_t bytes) {
   return VIHMC_OK;
 }
 
-template <int W, int NH>
-static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
+template <int W>
+static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
   const int threads = a.warps_per_block * 32;
   if (op == kOpLogpGrad) {
-    auto k = mlp_small_logp_grad_kernel<W, NH>;
+    auto k = mlp_small_logp_grad_kernel<W>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.logp, a.grad);
     VIHMC_LAUNCH_OK("mlp_small_logp_grad_kernel");
   } else if (op == kOpPredict) {
-    auto k = mlp_small_predict_kernel<W, NH>;
+    auto k = mlp_small_predict_kernel<W>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.out);
     VIHMC_LAUNCH_OK("mlp_small_predict_kernel");
   } else {
-    auto k = mlp_small_sample_kernel<W, NH>;
+    auto k = mlp_small_sample_kernel<W>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.A);
     VIHMC_LAUNCH_OK("mlp_small_sample_kernel");
   }
   return VIHMC_OK;
-}
-
-template <int W>
-static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
-  switch (P.n_hidden) {
-    case 1: return launch_small_wn<W, 1>(op, P, a, st);
-    case 2: return launch_small_wn<W, 2>(op, P, a, st);
-    case 3: return launch_small_wn<W, 3>(op, P, a, st);
-    case 4: return launch_small_wn<W, 4>(op, P, a, st);
-  }
-  return fail(VIHMC_ERR_UNSUPPORTED, "no small-MLP instantiation for %d hidden layers", P.n_hidden);
 }
 
 }  // namespace vihmc
