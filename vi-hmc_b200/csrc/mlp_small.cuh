@@ -27,6 +27,10 @@ namespace vihmc {
 
 constexpr int kMaxHidden = 4;
 
+#ifndef VIHMC_SMALL_MINBLOCKS
+#define VIHMC_SMALL_MINBLOCKS 6   // register budget of the small-MLP kernels: 65536 / (128 * minblocks)
+#endif
+
 struct SmallLayout {
   // weight region (floats from the chain base): row-major [unit][row stride] tables, and for the
   // hidden->hidden layers a transposed copy [input unit][WSW] used by the backward data pass
@@ -125,19 +129,13 @@ __device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long l
   }
 }
 
-// tanh with tanhf-class accuracy and no divergent branch: |x| < 0.55 minimax odd polynomial (fp32 max
-// rel. error 6.5e-8), otherwise 1 - 2/(exp(2|x|)+1) on ex2.approx / rcp.approx (<= 1.8e-7).
+// tanh(x) = sign(x) (1 - 2 / (exp(2|x|) + 1)) on ex2.approx / rcp.approx: 8 instructions, no branch.
+// Absolute error <= ~1.2e-7 (one ulp at 1.0) over the whole range -- the same as tanhf's large-|x|
+// branch; near 0 the RELATIVE error grows like 6e-8/|x|, which is harmless here because activations only
+// ever enter sums against O(1) terms (checked by the rtol-1e-5 parity tests against the reference).
 __device__ __forceinline__ float tanh_sel(float x) {
-  const float ax = fabsf(x), x2 = x * x;
-  float p = -6.6157488502e-03f;
-  p = fmaf(p, x2, 2.1312740519e-02f);
-  p = fmaf(p, x2, -5.3910065611e-02f);
-  p = fmaf(p, x2, 1.3333117609e-01f);
-  p = fmaf(p, x2, -3.3333332045e-01f);
-  const float small = fmaf(x * x2, p, x);
-  const float e = __expf(2.0f * ax);
-  const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
-  return ax < 0.55f ? small : big;
+  const float e = __expf(2.0f * fabsf(x));
+  return copysignf(fmaf(-2.0f, __fdividef(1.0f, e + 1.0f), 1.0f), x);
 }
 
 // in: z[8] pre-activations; out: z[8] = act(z), da[8] = act'(z)
@@ -165,6 +163,9 @@ __device__ __forceinline__ void activate8(int act, float (&z)[8], float (&da)[8]
   }
 }
 
+// act'(z) of a stored row: tanh and relu recompute it from the activation, sine reads the stored cos(z)
+__device__ __forceinline__ void load_dact8(int act, const float* h_row, const float* da_row, float (&da)[8]);
+
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -172,6 +173,22 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+__device__ __forceinline__ void load_dact8(int act, const float* h_row, const float* da_row, float (&da)[8]) {
+  if (act == VIHMC_ACT_SINE) {
+    load8(da_row, da);
+  } else {
+    float h[8];
+    load8(h_row, h);
+    if (act == VIHMC_ACT_TANH) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) da[t] = fmaf(-h[t], h[t], 1.0f);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) da[t] = h[t] > 0.0f ? 1.0f : 0.0f;
+    }
+  }
 }
 
 // acc[t] += sum_k wrow[k] * rows[k][t], t < 8: the weight row sits in registers, 8 independent chains
@@ -264,16 +281,25 @@ __device__ __forceinline__ float forward_chunk(float* sm, const SmallParams& P, 
     const float b = sm[L.bbase[0] + j];
 #pragma unroll
     for (int t = 0; t < 8; ++t) z[t] = b;
-    for (int k = 0; k < P.in_dim; ++k) {
-      const float w = sm[L.wbase[0] + j * L.ws[0] + k];
+    if (P.in_dim == 1) {  // the reference's nets: Linear(1, w0)
+      const float w = sm[L.wbase[0] + j * L.ws[0]];
       float r[8];
-      load8(act + L.xs + k * NCS + c0, r);
+      load8(act + L.xs + c0, r);
 #pragma unroll
       for (int t = 0; t < 8; ++t) z[t] = fmaf(w, r[t], z[t]);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < P.in_dim; ++k) {
+        const float w = sm[L.wbase[0] + j * L.ws[0] + k];
+        float r[8];
+        load8(act + L.xs + k * NCS + c0, r);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) z[t] = fmaf(w, r[t], z[t]);
+      }
     }
     activate8(P.act, z, da);
     store8(act + L.h + j * NCS + c0, z);
-    store8(act + L.da + j * NCS + c0, da);
+    if (P.act == VIHMC_ACT_SINE) store8(act + L.da + j * NCS + c0, da);
   }
   __syncwarp();
   for (int l = 1; l < P.n_hidden; ++l) {
@@ -285,7 +311,7 @@ __device__ __forceinline__ float forward_chunk(float* sm, const SmallParams& P, 
       dot_rows<W, NCS>(sm + L.wbase[l] + j * WSW, act + L.h + (l - 1) * W * NCS + c0, z);
       activate8(P.act, z, da);
       store8(act + L.h + (l * W + j) * NCS + c0, z);
-      store8(act + L.da + (l * W + j) * NCS + c0, da);
+      if (P.act == VIHMC_ACT_SINE) store8(act + L.da + (l * W + j) * NCS + c0, da);
     }
     __syncwarp();
   }
@@ -313,7 +339,7 @@ __device__ __forceinline__ void backward_chunk(float* sm, const SmallParams& P, 
     float dO[8], da[8], dz[8];
     const float wo = sm[L.wbase[P.n_hidden] + j];
     load8(act + L.dO + c0, dO);
-    load8(act + L.da + (top * W + j) * NCS + c0, da);
+    load_dact8(P.act, act + L.h + (top * W + j) * NCS + c0, act + L.da + (top * W + j) * NCS + c0, da);
 #pragma unroll
     for (int t = 0; t < 8; ++t) dz[t] = wo * dO[t] * da[t];
     store8(act + L.dz + (top * W + j) * NCS + c0, dz);
@@ -325,7 +351,7 @@ __device__ __forceinline__ void backward_chunk(float* sm, const SmallParams& P, 
 #pragma unroll
       for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
       dot_rows<W, NCS>(sm + L.tbase[l] + j * WSW, act + L.dz + l * W * NCS + c0, acc);
-      load8(act + L.da + ((l - 1) * W + j) * NCS + c0, da);
+      load_dact8(P.act, act + L.h + ((l - 1) * W + j) * NCS + c0, act + L.da + ((l - 1) * W + j) * NCS + c0, da);
 #pragma unroll
       for (int t = 0; t < 8; ++t) acc[t] *= da[t];
       store8(act + L.dz + ((l - 1) * W + j) * NCS + c0, acc);
@@ -334,9 +360,12 @@ __device__ __forceinline__ void backward_chunk(float* sm, const SmallParams& P, 
   }
 }
 
-// phase B: lane = sampled coordinate; accumulates d loglik / d q_i of the staged chunk into sm[g]
-template <int W>
-__device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int lane, bool first_chunk) {
+// phase B: lane = sampled coordinate; accumulates d loglik / d q_i of the staged chunk.  On the last
+// chunk the finished likelihood gradient of coordinate i goes straight to `consume(i, g_i)` (prior, kick,
+// drift, weight-table scatter: one pass, no round trip through sm[g]); earlier chunks park it in sm[g].
+template <int W, typename Consume>
+__device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int lane, bool first_chunk, bool last_chunk,
+                                        Consume&& consume) {
   constexpr int NC = (32 / W) * 8;
   const SmallLayout& L = P.lay;
   const float* act = sm + L.act_base;
@@ -354,15 +383,18 @@ __device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int lan
       acc2 = fmaf(a.z, b.z, acc2);
       acc3 = fmaf(a.w, b.w, acc3);
     }
-    const float gsum = (acc0 + acc1) + (acc2 + acc3);
-    sm[L.g + i] = first_chunk ? gsum : sm[L.g + i] + gsum;
+    float gsum = (acc0 + acc1) + (acc2 + acc3);
+    if (!first_chunk) gsum += sm[L.g + i];
+    if (last_chunk) consume(i, gsum);
+    else sm[L.g + i] = gsum;
   }
 }
 
-// Likelihood gradient w.r.t. every sampled coordinate into sm[g] (no prior yet); returns this lane's
-// share of the log-likelihood.  yv0 = the lane's target when the data fit one chunk.
-template <int W>
-__device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallParams& P, const Likelihood lik, int lane, float yv0) {
+// One gradient evaluation: consume(i, d loglik / d q_i) is called once per sampled coordinate (no prior
+// yet); returns this lane's share of the log-likelihood.  yv0 = the lane's target when N fits one chunk.
+template <int W, typename Consume>
+__device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallParams& P, const Likelihood lik, int lane, float yv0,
+                                                      Consume&& consume) {
   constexpr int NC = (32 / W) * 8;
   const SmallLayout& L = P.lay;
   float* act = sm + L.act_base;
@@ -383,7 +415,7 @@ __device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallPara
     }
     __syncwarp();
     backward_chunk<W>(sm, P, lane);
-    phase_b<W>(sm, P, lane, chunk == 0);
+    phase_b<W>(sm, P, lane, chunk == 0, chunk == n_chunks - 1, consume);
     __syncwarp();
   }
   return ll_lane;
@@ -393,7 +425,7 @@ __device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallPara
 // kernel 1: log-posterior value + gradient for C chains (vihmc_logp_grad, MLP small path)
 // ------------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(128) mlp_small_logp_grad_kernel(SmallParams P, long long C, const float* __restrict__ q,
+__global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C, const float* __restrict__ q,
                                                                   float* __restrict__ logp, float* __restrict__ grad) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -403,13 +435,12 @@ __global__ void __launch_bounds__(128) mlp_small_logp_grad_kernel(SmallParams P,
   float* sm = smem + (size_t)warp * L.total;
   const float yv0 = chain_init<W>(sm, P, q + chain * P.d, lane);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
-  const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0);
   float lp_lane = 0.0f;
-  for (int i = lane; i < (int)P.d; i += 32) {
+  const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0, [&](int i, float gl) {
     const float dq = sm[L.q + i] - sm[L.pmu + i], iv = sm[L.piv + i];
     lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
-    if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, sm[L.g + i]);
-  }
+    if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, gl);
+  });
   const float total = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + P.prior_log_norm * P.inv_prior_scale;
   if (lane == 0) logp[chain] = total;
 }
@@ -457,7 +488,7 @@ struct SampleArgs {
 };
 
 template <int W>
-__global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
+__global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long chain = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -516,15 +547,14 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
     const float half_eps = 0.5f * eps;
     float logp0 = 0.0f, logp1 = 0.0f, ke1 = 0.0f;
     for (int s = 0; s <= nsteps; ++s) {
-      const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0);
       const bool first = s == 0, last = s == nsteps;
       const float kick = first ? half_eps : eps;
       float lp_lane = 0.0f, ke_lane = 0.0f;
-      for (int i = lane; i < d; i += 32) {
+      const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0, [&](int i, float gl) {
         const float qv0 = sm[L.q + i];
         const float dq = qv0 - sm[L.pmu + i], iv = sm[L.piv + i];
         lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
-        const float gi = fmaf(-dq * iv, P.inv_prior_scale, sm[L.g + i]);
+        const float gi = fmaf(-dq * iv, P.inv_prior_scale, gl);
         float pv = axpy_unfused(kick, gi, sm[L.p + i]);
         if (last) {
           // hamiltorch: p += eps*g inside the loop, then ret_momenta[-1] - 0.5*eps*g (separately rounded)
@@ -538,7 +568,7 @@ __global__ void __launch_bounds__(128) mlp_small_sample_kernel(SmallParams P, Sa
           if (wt >= 0) sm[wt] = qv;
         }
         sm[L.p + i] = pv;
-      }
+      });
       if (first || last) {
         const float lp = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + log_norm;
         if (first) logp0 = lp;

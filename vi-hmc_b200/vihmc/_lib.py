@@ -7,7 +7,7 @@ import os
 
 MAX_LAYERS = 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvihmc.so")
+LIB_PATH = os.environ.get("VIHMC_LIB_PATH", os.path.join(_HERE, "libvihmc.so"))  # override: A/B builds only
 
 
 class VihmcError(RuntimeError):
