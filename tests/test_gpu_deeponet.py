@@ -194,3 +194,22 @@ def test_mh_accept_select():
     for c, a in enumerate(want):
         exp = q_prop[c] if a else fb0[c]
         assert torch.equal(q_cur[c], exp) and torch.equal(stored[c], exp) and torch.equal(q_fb[c], exp)
+
+
+def test_deeponet_tensor_core_shapes_vs_fp64_oracle():
+    """Shipped 172 401-parameter net at N=200, P=2601: every GEMM (layers, head with M=200 / N=2601, both backward
+    products, the K=2601 weight-gradient GEMMs, which take the split-K route) runs on the tcgen05 3xTF32 kernel.
+    Checked against the fp64 oracle at rtol 2e-5 (the fp32 reference itself sits ~1e-5 from fp64 at this size)."""
+    from vihmc.spec import DeepONetArch
+
+    arch = DeepONetArch()
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=200, n_t=51, n_x=51, seed=5)
+    spec = LogProbSpec(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
+    closure = oc.DeepONetLogProb(x1=x1.unsqueeze(1), x2=x2.unsqueeze(0), y=y, dtype=torch.float64)
+    rs = np.random.RandomState(0)
+    q = (theta.numpy()[None] + 0.02 * rs.randn(2, arch.num_params)).astype(np.float32)
+    logp, grad = engine.logp_grad(spec, torch.from_numpy(q))
+    for c in range(2):
+        lp, gr = oc.value_and_grad(closure, torch.from_numpy(q[c]).double())
+        assert abs(float(logp[c]) - float(lp)) <= RTOL * abs(float(lp)), (float(logp[c]), float(lp))
+        _close(grad[c].cpu().numpy(), gr.numpy(), rtol=2e-5)

@@ -18,7 +18,10 @@
 //   G   [Cb, N, P]         d loglik / d output (the only [N,P]-sized per-chain buffer)
 //   dz0/dz1 [Cb, R, w]     ping-pong pre-activation gradients, R = max(N, P)
 //   dWf [Cb, D]            gradient w.r.t. the full weight vector; gathered to grad[C, d] at the end
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace vihmc {
 
@@ -27,26 +30,6 @@ int launch_scatter(const float*, const long long*, const float*, float*, long lo
 // =============================================================================================
 // batched SGEMM  C[b] = opA(A[b]) (MxK) * opB(B[b]) (KxN), generic element strides, fused epilogues
 // =============================================================================================
-enum Epilogue {
-  EPI_STORE = 0,      // C = acc
-  EPI_BIAS_ACT = 1,   // C = act(acc + bias[n])           (act = identity when act < 0)
-  EPI_DACT = 2,       // C = acc * act'(aux[m,n])         (aux = the layer's stored activation)
-  EPI_HEAD = 3        // r = acc + bias0 - Y[m,n]; C = -prec r; partial sums of loglik and of C per CTA
-};
-
-struct GemmArgs {
-  const float* A; long long a_bs, a_sm, a_sk;
-  const float* B; long long b_bs, b_sk, b_sn;
-  float* C; long long c_bs, ldc;
-  int M, N, K;
-  // epilogue operands
-  const float* bias; long long bias_bs;   // [N] per batch (EPI_BIAS_ACT) or scalar per batch (EPI_HEAD)
-  const float* aux; long long aux_bs, ld_aux;  // activation (EPI_DACT) or Y (EPI_HEAD; aux_bs = 0: shared)
-  int act;
-  float ll_const, half_prec, prec;
-  float* part_ll; float* part_g;          // [batch, tiles] (EPI_HEAD)
-};
-
 constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8, GEMM_THREADS = 256;
 
 template <int EPI>
@@ -167,10 +150,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_batched_kernel(GemmArgs g)
   }
 }
 
+// VIHMC_DENSE_SIMT=1 keeps every GEMM on the FP32-SIMT kernel (A/B runs and the baseline the
+// tensor-core kernel is checked against)
+static bool tensor_cores_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("VIHMC_DENSE_SIMT");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
+
 template <int EPI>
-static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
+static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scratch = nullptr) {
   if (g.M < 1 || g.N < 1 || g.K < 1 || batch < 1) return fail(VIHMC_ERR_INVALID, "gemm: empty problem");
   if (batch > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch > 65535");
+  if (tensor_cores_enabled() && tc_gemm_eligible(g)) return launch_tc_gemm<EPI>(g, batch, st, scratch);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
   sgemm_batched_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
   VIHMC_LAUNCH_OK("sgemm_batched_kernel");
@@ -313,7 +307,7 @@ struct DensePlan {
   int K;            // DeepONet: output_neurons
   long long head_tiles, loss_tiles;
   // per-chain float counts
-  long long act_a_floats, act_b_floats, per_chain_floats;
+  long long act_a_floats, act_b_floats, per_chain_floats, scratch_per_chain;
   long long shared_floats;  // trunk features
 };
 
@@ -346,7 +340,16 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
   pl.loss_tiles = (pl.N + 255) / 256;
   const long long tiles = pl.deeponet ? pl.head_tiles : pl.loss_tiles;
   const long long G = pl.deeponet ? pl.N * pl.P : pl.N;
-  pl.per_chain_floats = 2 * pl.D + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P;
+  pl.scratch_per_chain = 0;   // split-K partials of the largest weight-gradient GEMM
+  for (int l = 0; l < pl.a.n_layers; ++l) {
+    const long long f = splitk_scratch_floats(pl.a.dims[l], pl.a.in_of(l), (int)pl.N, 1);
+    pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
+  }
+  for (int l = 0; l < pl.b.n_layers; ++l) {
+    const long long f = splitk_scratch_floats(pl.b.dims[l], pl.b.in_of(l), (int)pl.P, 1);
+    pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
+  }
+  pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.D + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P;
   pl.shared_floats = pl.deeponet ? pl.P * 5 + 64 : 64;
   return VIHMC_OK;
 }
@@ -416,7 +419,7 @@ static int stack_forward(const Stack& s, const float* input, long long R, const 
 
 // backward of one stack: dz holds d/d(pre-activation of the last layer) [Cb, R, dims[last]] on entry.
 static int stack_backward(const Stack& s, const float* input, long long R, const float* Wf, float* dWf, long long D,
-                          float* const* acts, float* dz_cur, float* dz_other, int act, int Cb, cudaStream_t st) {
+                          float* const* acts, float* dz_cur, float* dz_other, int act, int Cb, cudaStream_t st, float* scratch) {
   for (int l = s.n_layers - 1; l >= 0; --l) {
     const int in = s.in_of(l), out = s.dims[l];
     // dW[o,i] = sum_r dz[r,o] * a_in[r,i]
@@ -425,7 +428,7 @@ static int stack_backward(const Stack& s, const float* input, long long R, const
     g.B = l == 0 ? input : acts[l - 1]; g.b_bs = l == 0 ? 0 : R * in; g.b_sk = in; g.b_sn = 1;
     g.C = dWf + s.w_off[l]; g.c_bs = D; g.ldc = in;
     g.M = out; g.N = in; g.K = (int)R;
-    if (int rc = launch_gemm<EPI_STORE>(g, Cb, st)) return rc;
+    if (int rc = launch_gemm<EPI_STORE>(g, Cb, st, scratch)) return rc;
     if (s.has_bias[l]) {
       colsum_kernel<<<dim3((out + 31) / 32, Cb), dim3(32, 8), 0, st>>>(dz_cur, R * out, R, out, out, dWf + s.b_off[l], D);
       VIHMC_LAUNCH_OK("colsum_kernel");
@@ -495,6 +498,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     float* part_ll = bb.take((long long)Cb * tiles);
     float* part_g = bb.take((long long)Cb * tiles);
     float* loglik = bb.take(Cb);
+    float* scratch = pl.scratch_per_chain > 0 ? bb.take((long long)Cb * pl.scratch_per_chain) : nullptr;
     const float* qb = q + c0 * d;
 
     if (int rc = launch_scatter(p->frozen, reinterpret_cast<const long long*>(p->sens_ind), qb, Wf, Cb, D, d, st)) return rc;
@@ -527,14 +531,14 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
         h.B = Tout; h.b_bs = P * K; h.b_sk = K; h.b_sn = 1;
         h.C = dz0; h.c_bs = N * K; h.ldc = K; h.M = (int)N; h.N = K; h.K = (int)P;
         if (int rc = launch_gemm<EPI_STORE>(h, Cb, st)) return rc;
-        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st)) return rc;
+        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
         // dTout[p,k] = sum_n G[n,p] Bout[n,k]
         GemmArgs t{};
         t.A = G; t.a_bs = N * P; t.a_sm = 1; t.a_sk = P;
         t.B = Bout; t.b_bs = N * K; t.b_sk = K; t.b_sn = 1;
         t.C = dz0; t.c_bs = P * K; t.ldc = K; t.M = (int)P; t.N = K; t.K = (int)N;
         if (int rc = launch_gemm<EPI_STORE>(t, Cb, st)) return rc;
-        if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, D, acts_b, dz0, dz1, p->act, Cb, st)) return rc;
+        if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, D, acts_b, dz0, dz1, p->act, Cb, st, scratch)) return rc;
       }
     } else {
       const float* O = acts_a[pl.a.n_layers - 1];
@@ -546,7 +550,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
       VIHMC_LAUNCH_OK("mlp_loss_kernel");
       reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, tiles, Cb, loglik, 1);
       if (grad != nullptr)
-        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st)) return rc;
+        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
     }
     finalize_kernel<<<Cb, 256, 0, st>>>(dWf, reinterpret_cast<const long long*>(p->sens_ind), qb, p->prior_mu, p->prior_sigma,
                                         p->prior_sigma_scalar, 1.0f / p->prior_scale, p->prior_log_norm, loglik, D, d,
