@@ -17,8 +17,9 @@
 //     why the operands are not staged with TMA: the split needs the values in registers anyway.
 //   * two smem stages; thread 0 issues 3 MMAs per 8-deep k-step and commits to the stage's mbarrier;
 //     the next tile's global loads are in flight while the tensor core works.
-//   * epilogue: 8 warps read the accumulator with tcgen05.ld (warp w -> TMEM lanes 32*(w%4).., column
-//     half w/4), apply bias+act / act' / Gaussian residual, and write C.
+//   * epilogue: 8 warps read the accumulators with tcgen05.ld (warp w -> TMEM lanes 32*(w%4).., column
+//     half w/4) into a shared-memory tile, then apply bias+act / act' / Gaussian residual and write C
+//     row-wise so every warp instruction touches contiguous memory.
 #pragma once
 #include "common.cuh"
 
@@ -56,7 +57,9 @@ constexpr int LBO = 128;                       // bytes between the K-chunks of 
 constexpr int SBO = CHUNKS * 128;              // bytes between 8-row groups
 constexpr int TILE_BYTES = (BM / 8) * SBO;     // 8 KB: one 128 x 16 fp32 operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
+constexpr int TILE_LD = BN + 4;                 // epilogue staging tile row stride (floats): conflict-free float4 rows
+constexpr int EPI_BYTES = BM * TILE_LD * 4;     // 67,584 B >= the two operand stages
+constexpr int SMEM_BYTES = (EPI_BYTES > STAGES * STAGE_BYTES ? EPI_BYTES : STAGES * STAGE_BYTES) + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -162,8 +165,8 @@ template <int EPI>
 __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_vec, int b_vec) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 64);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SMEM_BYTES - 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BYTES - 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool split = (EPI == EPI_STORE) && g.splits > 1;
   const int b = split ? (int)blockIdx.z / g.splits : (int)blockIdx.z;
@@ -236,52 +239,71 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   mbar_wait(&mbar[(nk - 1) & 1], (uint32_t)((nk - 1) >> 1) & 1u);   // commits complete in order: everything is done
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---------------- epilogue: thread -> one accumulator row, 64 columns in chunks of 8 ----------------
-  const int q = warp & 3, half = warp >> 2;
-  const int m = m0 + q * 32 + lane;
+  // ---------------- epilogue ----------------
+  // phase 1: TMEM -> registers -> shared tile [128][TILE_LD] (thread = one accumulator row, 8 columns per ld).
+  // phase 2: coalesced pass: warp w owns rows w, w+8, ...; a warp instruction touches 512 contiguous bytes of
+  // C / aux (each lane 4 columns), instead of 32 different rows as a row-per-thread epilogue would.
+  float* tile = reinterpret_cast<float*>(smem);   // operand stages are dead: every MMA has completed
+  {
+    const int q = warp & 3, half = warp >> 2;
+    float* trow = tile + (q * 32 + lane) * TILE_LD + half * (BN / 2);
+#pragma unroll 2
+    for (int cc = 0; cc < BN / 2; cc += 8) {
+      uint32_t r[8], rc[8];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + cc);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(taddr));
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
+                   : "r"(taddr + (uint32_t)BN));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);   // main + corrections (RN)
+      *reinterpret_cast<float4*>(trow + cc) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(trow + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  __syncthreads();
   float* __restrict__ Cb = g.C + (long long)b * g.c_bs;
   const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)b * g.bias_bs) : 0.0f;
+  const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs : nullptr;
+  const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
   float ll_acc = 0.0f, g_acc = 0.0f;
 #pragma unroll 1
-  for (int cc = 0; cc < BN / 2; cc += 8) {
-    const int col = half * (BN / 2) + cc;
-    uint32_t r[8], rc[8];
-    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
-                 : "r"(taddr + (uint32_t)BN));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (m < g.M) {
+  for (int r = warp; r < BM; r += THREADS / 32) {
+    const int m = m0 + r;
+    if (m >= g.M) break;
+    float* crow = Cb + (long long)m * g.ldc + n0;
+    const float* arow = auxb ? auxb + (long long)m * g.ld_aux + n0 : nullptr;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = n0 + col + j;
-        if (n >= g.N) continue;
-        float v = __uint_as_float(r[j]) + __uint_as_float(rc[j]);   // main + corrections, rounded to nearest
-        if (EPI == EPI_BIAS_ACT) {
-          v += __ldg(g.bias + (long long)b * g.bias_bs + n);
-          if (g.act == VIHMC_ACT_TANH) v = tanhf(v);
-          else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
-        } else if (EPI == EPI_DACT) {
-          const float a = __ldg(g.aux + (long long)b * g.aux_bs + (long long)m * g.ld_aux + n);
-          v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - a * a) : (a > 0.0f ? 1.0f : 0.0f);
-        } else if (EPI == EPI_HEAD) {
-          const float res = v + bias0 - __ldg(g.aux + (long long)b * g.aux_bs + (long long)m * g.ld_aux + n);
-          ll_acc += g.ll_const - g.half_prec * res * res;
-          v = -g.prec * res;
-          g_acc += v;
-        }
-        Cb[(long long)m * g.ldc + n] = v;
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;           // 128 contiguous bytes per warp instruction
+      const int n = n0 + c;
+      if (n >= g.N) continue;
+      float v = tile[r * TILE_LD + c];
+      if (EPI == EPI_BIAS_ACT) {
+        v += __ldg(biasb + n);
+        if (g.act == VIHMC_ACT_TANH) v = tanhf(v);
+        else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+      } else if (EPI == EPI_DACT) {
+        const float a = __ldg(arow + c);
+        v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - a * a) : (a > 0.0f ? 1.0f : 0.0f);
+      } else if (EPI == EPI_HEAD) {
+        const float res = v + bias0 - __ldg(arow + c);
+        ll_acc += g.ll_const - g.half_prec * res * res;
+        v = -g.prec * res;
+        g_acc += v;
       }
+      crow[c] = v;
     }
   }
   if (EPI == EPI_HEAD) {
-    float* red = reinterpret_cast<float*>(smem);   // operand tiles are dead: every MMA has completed
+    float* red = reinterpret_cast<float*>(smem);
     ll_acc = warp_sum(ll_acc);
     g_acc = warp_sum(g_acc);
-    __syncthreads();
+    __syncthreads();   // every warp is done reading the staged tile
     if (lane == 0) { red[warp] = ll_acc; red[8 + warp] = g_acc; }
     __syncthreads();
     if (tid == 0) {
@@ -323,7 +345,7 @@ inline long long splitk_scratch_floats(int M, int N, int K, int batch) {
 }
 
 // shapes the tensor-core kernel is used for; everything else stays on the FP32-SIMT kernel
-inline bool tc_gemm_eligible(const GemmArgs& g) { return g.M >= 32 && g.N >= 16 && g.K >= 16; }
+inline bool tc_gemm_eligible(const GemmArgs& g) { return g.M >= 32 && g.K >= 16 && (g.N >= 16 || g.K >= 512); }
 
 template <int EPI>
 static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch = nullptr) {
