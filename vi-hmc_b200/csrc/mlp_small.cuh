@@ -129,15 +129,6 @@ __device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long l
   }
 }
 
-// tanh(x) = sign(x) (1 - 2 / (exp(2|x|) + 1)) on ex2.approx / rcp.approx: 8 instructions, no branch.
-// Absolute error <= ~1.2e-7 (one ulp at 1.0) over the whole range -- the same as tanhf's large-|x|
-// branch; near 0 the RELATIVE error grows like 6e-8/|x|, which is harmless here because activations only
-// ever enter sums against O(1) terms (checked by the rtol-1e-5 parity tests against the reference).
-__device__ __forceinline__ float tanh_sel(float x) {
-  const float e = __expf(2.0f * fabsf(x));
-  return copysignf(fmaf(-2.0f, __fdividef(1.0f, e + 1.0f), 1.0f), x);
-}
-
 // in: z[8] pre-activations; out: z[8] = act(z), da[8] = act'(z)
 __device__ __forceinline__ void activate8(int act, float (&z)[8], float (&da)[8]) {
   if (act == VIHMC_ACT_TANH) {

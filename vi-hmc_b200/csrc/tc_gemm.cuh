@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
     if (kt >= 2) mbar_wait(&mbar[s], (uint32_t)((kt >> 1) - 1) & 1u);   // the MMAs that read this stage are done
     stash(st, st + TILE_BYTES, tid, ra);
     stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, rb);
-    if (kt + 1 < nk) {
+    if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
       la.fetch((kt + 1) * BK, tid, ra);
       lb.fetch((kt + 1) * BK, tid, rb);
     }
@@ -271,6 +271,12 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs : nullptr;
   const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
   float ll_acc = 0.0f, g_acc = 0.0f;
+  float bias_r[4] = {0.f, 0.f, 0.f, 0.f};   // this lane's four columns: loaded once, not once per row
+  if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + lane + 32 * j < g.N) bias_r[j] = __ldg(biasb + n0 + lane + 32 * j);
+  }
 #pragma unroll 1
   for (int r = warp; r < BM; r += THREADS / 32) {
     const int m = m0 + r;
@@ -284,8 +290,8 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
       if (n >= g.N) continue;
       float v = tile[r * TILE_LD + c];
       if (EPI == EPI_BIAS_ACT) {
-        v += __ldg(biasb + n);
-        if (g.act == VIHMC_ACT_TANH) v = tanhf(v);
+        v += bias_r[j];
+        if (g.act == VIHMC_ACT_TANH) v = tanh_sel(v);   // 8 instructions, abs. error ~1.2e-7 (see common.cuh)
         else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
       } else if (EPI == EPI_DACT) {
         const float a = __ldg(arow + c);
