@@ -205,7 +205,7 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
 
     def launch(n_samples, seed):
         return engine.run_sampler([prep], q0, n_samples, L_STEPS, STEP_SIZE, burn=0, seed=seed, chain_offset=chain0,
-                                  diagnostics=False, to_host=False)
+                                  diagnostics=True, to_host=False)
 
     # ---- device-timed: inputs resident in HBM, one persistent launch of `steps` iterations ----
     launch(warmup, seed=1)
@@ -227,7 +227,25 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
     ms = float(t.item())
     evals = world * CHAINS_PER_GPU * steps * (L_STEPS + 1)
     value = evals / (ms * 1e-3)
-    acc_rate = float((res.samples[1:] != res.samples[:-1]).any(dim=2).float().mean()) if steps > 1 else float("nan")
+    acc_rate = float(res.accepted.float().mean())
+    # ESS/s (the metric's second half): rank-normalised split-R-hat / bulk-ESS (vihmc.diagnostics, Vehtari et al. 2021)
+    # over the post-burn draws of THIS rank's chains (burn = steps // 5 as cfg.burn = num_samples // 5), per second of
+    # the device-timed run; summed over ranks because chains are independent.
+    ess = None
+    if steps >= 40:
+        from vihmc import diagnostics
+        burn_rows = steps // 5
+        summ = diagnostics.summarize(res.samples[burn_rows:], logp=res.logp[burn_rows:])
+        t_ess = torch.tensor([summ["ess_bulk_min"], summ["ess_bulk_median"], summ["ess_bulk_logp"]], device=dev, dtype=torch.float64)
+        t_rhat = torch.tensor([summ["rhat_max"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_ess, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_rhat, op=dist.ReduceOp.MAX)
+        ess = {"definition": "bulk-ESS, rank-normalised, split chains; min / median over the d sampled coordinates, chains pooled",
+               "post_burn_draws": int(summ["draws"]), "chains": int(summ["chains"]) * world,
+               "ess_bulk_min": float(t_ess[0]), "ess_bulk_median": float(t_ess[1]), "ess_bulk_logp": float(t_ess[2]),
+               "rhat_max": float(t_rhat[0]),
+               "ess_min_per_sec": float(t_ess[0]) / (ms * 1e-3), "ess_median_per_sec": float(t_ess[1]) / (ms * 1e-3)}
 
     # ---- end to end through the public API: host tensors in, host samples out, every call ----
     samplers.sample(spec, q0_host, num_samples=warmup, num_steps_per_sample=L_STEPS, step_size=STEP_SIZE, seed=3,
@@ -279,6 +297,7 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
         "gpu_launches": 1,
         "clocks": clk.summary(),
         "acceptance_rate": acc_rate,
+        "ess": ess,
     }
     if world > 1:
         dist.destroy_process_group()

@@ -260,3 +260,47 @@ def test_reference_style_call_returns_list():
     many = samplers.sample(spec, torch.from_numpy(case["q"][0]), num_samples=6, num_steps_per_sample=4, step_size=5e-4,
                            num_chains=5, burn=2)
     assert many.shape == (4, 5, case["d"])
+
+
+def test_law_of_the_chain_matches_oracle_sampler():
+    """Distributional parity ("posterior predictive mean/variance within Monte Carlo standard error"): engine and oracle
+    implement the same Markov kernel from the same initial law, so after n iterations the state has the same law.
+    4096 engine chains (Philox streams) vs 32 oracle chains (torch RNG): the predictive mean at 6 validation inputs must
+    agree within 4 standard errors of the small oracle ensemble, the predictive spread within a factor, and the
+    acceptance rates within binomial error."""
+    from vihmc import synth
+
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    d, S, L, eps = case["d"], 10, 6, 1e-3
+    mu, sg = case["mu"].numpy()[case["ind"]], case["sigma"].numpy()[case["ind"]]
+    _, _, x_val, _ = synth.bnn_data()
+    xs = x_val[::50]                                              # 6 validation inputs
+    vspec = __import__("dataclasses").replace(spec, x=xs, y=torch.zeros(len(xs), 1))
+
+    def starts(n, seed):
+        return torch.from_numpy((mu[None] + sg[None] * np.random.RandomState(seed).randn(n, d)).astype(np.float32))
+
+    Cg, Co = 4096, 32
+    res = engine.run_sampler([spec], starts(Cg, 1), S, L, eps, seed=11)
+    f_gpu = engine.predict(vspec, res.samples[-1]).cpu().double()          # [Cg, 6] predictions of the final states
+    acc_gpu = float(res.accepted.float().mean())
+
+    closure = cases.bnn_oracle(case)
+    gen = torch.Generator().manual_seed(5)
+    finals, accs = [], []
+    q0o = starts(Co, 2)
+    for c in range(Co):
+        tr = {}
+        out = hr.sample(closure, q0o[c], num_samples=S, num_steps_per_sample=L, step_size=eps, generator=gen, trace=tr)
+        finals.append(out[-1])
+        accs += tr["accept"]
+    f_ora = torch.stack([closure.forward(q.detach(), x=xs)[:, 0] for q in finals]).double().detach()   # [Co, 6]
+    se = f_ora.std(0) / np.sqrt(Co)
+    z = (f_gpu.mean(0) - f_ora.mean(0)) / se
+    assert float(z.abs().max()) < 4.0, z
+    ratio = f_gpu.std(0) / f_ora.std(0)
+    assert float(ratio.min()) > 0.6 and float(ratio.max()) < 1.6, ratio
+    p = acc_gpu
+    assert abs(np.mean(accs) - p) < 4 * np.sqrt(max(p * (1 - p), 0.01) / len(accs)) + 0.02

@@ -213,3 +213,28 @@ def test_deeponet_tensor_core_shapes_vs_fp64_oracle():
         lp, gr = oc.value_and_grad(closure, torch.from_numpy(q[c]).double())
         assert abs(float(logp[c]) - float(lp)) <= RTOL * abs(float(lp)), (float(logp[c]), float(lp))
         _close(grad[c].cpu().numpy(), gr.numpy(), rtol=2e-5)
+
+
+def test_data_sharded_sampler_equals_general_sampler():
+    """cfg5 mode (rows sharded, gradient all-reduce) in a single process: the Python-orchestrated loop over the C-ABI
+    building blocks must reproduce vihmc_sample on the same problem; and two half-data shards with prior_scale = 2
+    must sum to the full log-posterior (what the all-reduce computes across ranks)."""
+    from vihmc import dist as vd
+
+    arch = MLPArch(in_dim=1, widths=(64, 64), out_dim=1, act="tanh", last_bias=True)
+    x, y = synth.wide_bnn_data(n=500, seed=1)
+    spec = LogProbSpec(arch=arch, x=x, y=y, loss="NLL", tau_out=0.0025, prior_sigma_scalar=1.0)
+    q0 = synth.default_linear_init(arch, seed=2).unsqueeze(0).repeat(3, 1)
+    q0[1:] += 0.02 * torch.from_numpy(np.random.RandomState(3).randn(2, arch.num_params).astype(np.float32))
+    kw = dict(num_samples=4, num_steps=5, step_size=2e-5, burn=1, seed=9)
+    a = vd.sample_data_sharded(vd.shard_spec_rows(spec, 0, 1), q0, **kw)
+    b = engine.run_sampler([spec], q0, force_general=True, **kw)
+    assert torch.equal(a["accepted"].cpu(), b.accepted)
+    np.testing.assert_allclose(a["samples"].cpu().numpy(), b.samples.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(a["hamiltonians"].cpu().numpy(), b.hamiltonians.numpy(), rtol=1e-6)
+    # shard sum == full (the quantity the all-reduce produces)
+    lp_full, g_full = engine.logp_grad(spec, q0)
+    parts = [engine.logp_grad(vd.shard_spec_rows(spec, r, 2), q0) for r in range(2)]
+    np.testing.assert_allclose((parts[0][0] + parts[1][0]).cpu().numpy(), lp_full.cpu().numpy(), rtol=2e-6)
+    gs = (parts[0][1] + parts[1][1]).cpu().numpy()
+    np.testing.assert_allclose(gs, g_full.cpu().numpy(), rtol=2e-5, atol=2e-5 * np.abs(gs).max())

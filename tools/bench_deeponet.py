@@ -35,13 +35,9 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     arch = DeepONetArch()
-    # teacher targets are irrelevant for timing: cheap synthetic data of the right shape
     rs = np.random.RandomState(0)
     P = a.nt * a.nx
-    x1 = torch.from_numpy(0.1 * rs.randn(a.n, arch.in_branch).astype(np.float32))
-    x2 = torch.from_numpy(synth.trunk_grid(a.nt, a.nx).astype(np.float32))
-    y = torch.from_numpy(0.2 * rs.randn(a.n, P).astype(np.float32))
-    theta = torch.from_numpy((0.1 * rs.randn(arch.num_params)).astype(np.float32))
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=a.n, n_t=a.nt, n_x=a.nx, seed=0)   # SURVEY 8(d) cfg3 data
     kw = dict(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
     if a.vi:
         mu, sigma, ind = synth.deeponet_vi_artifacts(theta, 0.10, seed=1)

@@ -95,3 +95,75 @@ def sample_sharded(specs, q0_all: torch.Tensor, total_chains: int, burn_in_draws
         out["logp"] = gather_chains(res.logp, total_chains) if res.logp is not None else None
         out["accepted"] = gather_chains(res.accepted, total_chains) if res.accepted is not None else None
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# optional second mode (BASELINE.json configs[4]): data-sharded likelihood, gradient all-reduce
+# ------------------------------------------------------------------------------------------------
+def shard_spec_rows(spec, rank: Optional[int] = None, world_size: Optional[int] = None):
+    """Row shard of a LogProbSpec for this rank: training rows [r*N/G, (r+1)*N/G), prior divided by G.
+
+    Summing the shard log-posteriors over ranks gives the full log-posterior -- the same construction as the
+    reference's split closures (main_HMC_splitting.py:28-54, 253-254: equal row blocks, prior_scale = num_splits)."""
+    import dataclasses
+
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    start, n = shard_chains(spec.N, rank, world_size)   # same contiguous-block rule, applied to rows
+    return dataclasses.replace(spec, x=spec.x[start:start + n].contiguous(), y=spec.y[start:start + n].contiguous(),
+                               prior_scale=float(spec.prior_scale) * world_size)
+
+
+def sample_data_sharded(spec_local, q0: torch.Tensor, num_samples: int, num_steps: int, step_size: float, burn: int = 0,
+                        seed: int = 0, hamiltorch_fallback_rule: bool = True) -> Dict[str, torch.Tensor]:
+    """HMC where every rank holds ALL chains and a row shard of the data (spec_local = shard_spec_rows(spec)).
+
+    One exchange step per gradient evaluation: all_reduce(SUM) of the [C, d] gradients and the [C] log-posteriors;
+    everything else is identical on every rank (same Philox streams), so all ranks make the same accept/reject
+    decisions and hold the same samples.  The [C, d] arithmetic runs in the C-ABI building blocks
+    (vihmc_logp_grad, vihmc_leapfrog_update, vihmc_momentum_philox, vihmc_mh_accept); torch does the collective
+    and the per-chain scalar adds.  Leapfrog order and rounding as in vihmc_sample / hamiltorch."""
+    from . import engine
+
+    rank, w = world()
+    prep = engine.prepare(spec_local)
+    dev = prep.device
+    d = prep.spec.d
+    q0d = q0.reshape(-1, d).to(device=dev, dtype=torch.float32).contiguous()
+    C = q0d.shape[0]
+    rows = num_samples - burn
+    if rows < 1:
+        raise RuntimeError("burn must be less than num_samples.")
+    samples = torch.empty((rows, C, d), dtype=torch.float32, device=dev)
+    samples[0] = q0d
+    accepted = torch.empty((num_samples, C), dtype=torch.uint8, device=dev)
+    ham = torch.empty((num_samples, C, 2), dtype=torch.float32, device=dev)
+    q_cur, q_fb = q0d.clone(), q0d.clone()
+
+    def grad(q):
+        lp, g = engine.logp_grad(prep, q)
+        if w > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            dist.all_reduce(lp, op=dist.ReduceOp.SUM)
+        return lp, g
+
+    for n in range(num_samples):
+        if hamiltorch_fallback_rule and n == burn + 1:
+            q_fb.copy_(q0d)
+        p = engine.momentum_philox(seed, n, 0, C, d, device=dev)
+        q = q_cur.clone()
+        lp, g = grad(q)
+        ke0 = engine.leapfrog_update(q, p, g, step_size, 0.0, 0.0, want_ke=True)     # kinetic energy of the fresh momentum
+        h0 = ke0 - lp
+        engine.leapfrog_update(q, p, g, step_size, 0.5, 1.0)
+        for s in range(1, num_steps + 1):
+            lp, g = grad(q)
+            engine.leapfrog_update(q, p, g, step_size, 1.0, 1.0 if s < num_steps else 0.0)
+        ke1 = engine.leapfrog_update(q, p, g, step_size, -0.5, 0.0, want_ke=True)
+        h1 = ke1 - lp
+        u = engine.uniform_philox(seed, n, 0, C, device=dev)
+        store = n > burn
+        engine.mh_accept(h0, h1, u, q, q_cur, q_fb, stored=samples[n - burn] if store else None, accepted=accepted[n])
+        ham[n, :, 0], ham[n, :, 1] = h0, h1
+    return {"samples": samples, "accepted": accepted, "hamiltonians": ham}
