@@ -1,4 +1,6 @@
 // Small-MLP path: host-side validation, kernel selection and launch geometry (kernels: mlp_small.cuh).
+#include <stdlib.h>
+
 #include "mlp_small.cuh"
 
 namespace vihmc {
@@ -63,15 +65,29 @@ int mlp_small_launch_w10(SmallOp, const SmallParams&, const SmallLaunch&, cudaSt
 int mlp_small_launch_w16(SmallOp, const SmallParams&, const SmallLaunch&, cudaStream_t);
 int mlp_small_launch_w32(SmallOp, const SmallParams&, const SmallLaunch&, cudaStream_t);
 
-// One warp per chain.  Few chains: 1 warp per CTA so the 148 SMs fill evenly; many chains: up to 4
-// warps per CTA so the 32-CTA/SM limit does not cap residency.
+// Geometry.  Warps per chain: 1.  Splitting a chain over 2 warps (VIHMC_SMALL_NW=2, kept for experiments) doubles
+// the resident warps but measured SLOWER on B200 at 1024 chains (313 M vs 489 M chain-grad-evals/s): the 64-thread
+// named barriers between phases and the halved per-lane ILP cost more than the extra TLP hides.  Chains per CTA: 1 for few chains so the
+// 148 SMs fill evenly, up to 4 warps per CTA for many chains so the 32-CTA/SM limit does not cap residency.
+static int warps_per_chain_for(long long C) {
+  static const int forced = []() {
+    const char* e = getenv("VIHMC_SMALL_NW");
+    return (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }();
+  if (forced) return forced;
+  (void)C;
+  return 1;
+}
+
 static void pick_geometry(const SmallLayout& L, long long C, SmallLaunch& a) {
   const size_t per_chain = (size_t)L.total * sizeof(float);
-  int wpb = 1;
-  while (wpb < 4 && C > (long long)148 * 24 * wpb && per_chain * (wpb * 2) <= 200u * 1024u) wpb *= 2;
-  a.warps_per_block = wpb;
-  a.blocks = (int)((C + wpb - 1) / wpb);
-  a.smem = per_chain * wpb;
+  const int nw = warps_per_chain_for(C);
+  int cpb = 1;
+  while (cpb * nw < 4 && C > (long long)148 * 24 * cpb && per_chain * (cpb * 2) <= 200u * 1024u) cpb *= 2;
+  a.warps_per_chain = nw;
+  a.chains_per_block = cpb;
+  a.blocks = (int)((C + cpb - 1) / cpb);
+  a.smem = per_chain * cpb;
   a.C = C;
 }
 

@@ -37,7 +37,7 @@ struct SmallLayout {
   int wbase[kMaxHidden + 1], ws[kMaxHidden + 1], bbase[kMaxHidden + 1], tbase[kMaxHidden + 1];
   int w_total;
   // per-coordinate state, each dp entries
-  int q, p, g, qf, pmu, piv, meta, wpos, wposT;
+  int q, p, g, qf, pmu, piv, meta, wpos, wposT, red;
   // activation region: rows of NCS floats
   int act_base, xs, h, da, dz, dO, ones;
   int NC, NCS, dp, total;
@@ -81,6 +81,7 @@ inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, lon
   L.meta = off; off += L.dp;
   L.wpos = off; off += L.dp;
   L.wposT = off; off += L.dp;
+  L.red = off; off += 8;      // cross-warp reduction slots (two warps per chain)
   L.NC = (32 / W) * 8;
   L.NCS = L.NC + 4;   // +4: eight different rows land in eight different bank groups
   L.act_base = off;
@@ -129,23 +130,24 @@ __device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long l
   }
 }
 
-// in: z[8] pre-activations; out: z[8] = act(z), da[8] = act'(z)
-__device__ __forceinline__ void activate8(int act, float (&z)[8], float (&da)[8]) {
+// in: z[P] pre-activations; out: z[P] = act(z), da[P] = act'(z)
+template <int P>
+__device__ __forceinline__ void activate8(int act, float (&z)[P], float (&da)[P]) {
   if (act == VIHMC_ACT_TANH) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < P; ++t) {
       z[t] = tanh_sel(z[t]);
       da[t] = fmaf(-z[t], z[t], 1.0f);
     }
   } else if (act == VIHMC_ACT_RELU) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < P; ++t) {
       da[t] = z[t] > 0.0f ? 1.0f : 0.0f;
       z[t] = z[t] > 0.0f ? z[t] : 0.0f;
     }
   } else {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < P; ++t) {
       float s, c;
       sincosf(z[t], &s, &c);
       z[t] = s;
@@ -155,36 +157,41 @@ __device__ __forceinline__ void activate8(int act, float (&z)[8], float (&da)[8]
 }
 
 // act'(z) of a stored row: tanh and relu recompute it from the activation, sine reads the stored cos(z)
-__device__ __forceinline__ void load_dact8(int act, const float* h_row, const float* da_row, float (&da)[8]);
-
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+template <int P>
+__device__ __forceinline__ void load8(const float* p, float (&v)[P]) {
+#pragma unroll
+  for (int c = 0; c < P / 4; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(p + 4 * c);
+    v[4 * c] = a.x; v[4 * c + 1] = a.y; v[4 * c + 2] = a.z; v[4 * c + 3] = a.w;
+  }
 }
-__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+template <int P>
+__device__ __forceinline__ void store8(float* p, const float (&v)[P]) {
+#pragma unroll
+  for (int c = 0; c < P / 4; ++c) *reinterpret_cast<float4*>(p + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
-__device__ __forceinline__ void load_dact8(int act, const float* h_row, const float* da_row, float (&da)[8]) {
+// act'(z) of a stored row: tanh and relu recompute it from the activation, sine reads the stored cos(z)
+template <int P>
+__device__ __forceinline__ void load_dact8(int act, const float* h_row, const float* da_row, float (&da)[P]) {
   if (act == VIHMC_ACT_SINE) {
     load8(da_row, da);
   } else {
-    float h[8];
+    float h[P];
     load8(h_row, h);
     if (act == VIHMC_ACT_TANH) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) da[t] = fmaf(-h[t], h[t], 1.0f);
+      for (int t = 0; t < P; ++t) da[t] = fmaf(-h[t], h[t], 1.0f);
     } else {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) da[t] = h[t] > 0.0f ? 1.0f : 0.0f;
+      for (int t = 0; t < P; ++t) da[t] = h[t] > 0.0f ? 1.0f : 0.0f;
     }
   }
 }
 
 // acc[t] += sum_k wrow[k] * rows[k][t], t < 8: the weight row sits in registers, 8 independent chains
-template <int W, int NCS>
-__device__ __forceinline__ void dot_rows(const float* wrow, const float* rows, float (&acc)[8]) {
+template <int W, int NCS, int P>
+__device__ __forceinline__ void dot_rows(const float* wrow, const float* rows, float (&acc)[P]) {
   constexpr int WSW = (W + 3) / 4 * 4;
   float w[WSW];
 #pragma unroll
@@ -194,39 +201,76 @@ __device__ __forceinline__ void dot_rows(const float* wrow, const float* rows, f
   }
 #pragma unroll
   for (int k = 0; k < W; ++k) {
-    float r[8];
+    float r[P];
     load8(rows + k * NCS, r);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[t] = fmaf(w[k], r[t], acc[t]);
+    for (int t = 0; t < P; ++t) acc[t] = fmaf(w[k], r[t], acc[t]);
   }
 }
 
-// point-mode staging of one data chunk: x columns, validity row; returns this lane's target
-template <int W>
-__device__ __forceinline__ float stage_chunk(float* sm, const SmallParams& P, int lane, int chunk) {
-  constexpr int NC = (32 / W) * 8, NCS = NC + 4;
+// ------------------------------------------------------------------------------------------------
+// chain-level geometry: NW warps cooperate on one chain (NW = 1: everything is warp-synchronous;
+// NW = 2: twice the warps per SM to hide latency when the chain count is small, 4 points per lane,
+// phases separated by a 64-thread named barrier)
+// ------------------------------------------------------------------------------------------------
+template <int W, int NW>
+struct Cfg {
+  static constexpr int T = 32 * NW;          // threads per chain
+  static constexpr int NC = (32 / W) * 8;    // data points per chunk
+  static constexpr int NCS = NC + 4;         // activation row stride
+  static constexpr int PPL = 8 / NW;         // data points per lane in unit mode
+  static constexpr int G = NC / PPL;         // point groups
+  static constexpr int WSW = (W + 3) / 4 * 4;
+  static_assert(G * W <= T, "unit-mode lanes exceed the chain's threads");
+};
+
+template <int NW>
+__device__ __forceinline__ void chain_sync(int bar) {
+  if (NW == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(32 * NW) : "memory");
+}
+
+// sum over all threads of the chain, same value on every thread (fixed order => reproducible)
+template <int NW>
+__device__ __forceinline__ float chain_sum(float v, float* red, int ct, int bar) {
+  v = warp_sum(v);
+  if (NW == 1) return v;
+  if ((ct & 31) == 0) red[ct >> 5] = v;
+  chain_sync<NW>(bar);
+  float s = 0.0f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s += red[w];
+  chain_sync<NW>(bar);
+  return s;
+}
+
+// point-mode staging of one data chunk: x columns, validity row; returns this thread's target
+template <int W, int NW>
+__device__ __forceinline__ float stage_chunk(float* sm, const SmallParams& P, int ct, int chunk) {
+  using C = Cfg<W, NW>;
   const SmallLayout& L = P.lay;
   float* act = sm + L.act_base;
   float yv = 0.0f;
-  if (lane < NC) {
-    const long long n = (long long)chunk * NC + lane;
+  if (ct < C::NC) {
+    const long long n = (long long)chunk * C::NC + ct;
     const bool valid = n < P.N;
-    for (int k = 0; k < P.in_dim; ++k) act[L.xs + k * NCS + lane] = valid ? __ldg(P.x + n * P.in_dim + k) : 0.0f;
-    act[L.ones + lane] = valid ? 1.0f : 0.0f;
+    for (int k = 0; k < P.in_dim; ++k) act[L.xs + k * C::NCS + ct] = valid ? __ldg(P.x + n * P.in_dim + k) : 0.0f;
+    act[L.ones + ct] = valid ? 1.0f : 0.0f;
     yv = valid ? __ldg(P.y + n) : 0.0f;
   }
   return yv;
 }
 
 // One-time per-chain setup: zero the weight tables, load frozen weights, decode coordinates, load
-// the prior and q (scattered into the tables).  Returns this lane's target when N fits one chunk.
-template <int W>
-__device__ float chain_init(float* sm, const SmallParams& P, const float* q_row, int lane) {
+// the prior and q (scattered into the tables).  Returns this thread's target when N fits one chunk.
+template <int W, int NW>
+__device__ float chain_init(float* sm, const SmallParams& P, const float* q_row, int ct, int bar) {
+  using C = Cfg<W, NW>;
   const SmallLayout& L = P.lay;
-  for (int i = lane; i < L.act_base; i += 32) sm[i] = 0.0f;
-  __syncwarp();
+  for (int i = ct; i < L.act_base; i += C::T) sm[i] = 0.0f;
+  chain_sync<NW>(bar);
   if (P.frozen != nullptr) {
-    for (long long f = lane; f < P.D; f += 32) {
+    for (long long f = ct; f < P.D; f += C::T) {
       int wpos, wposT, a, b;
       decode_coord(P, W, f, wpos, wposT, a, b);
       const float v = __ldg(P.frozen + f);
@@ -234,11 +278,11 @@ __device__ float chain_init(float* sm, const SmallParams& P, const float* q_row,
       if (wposT >= 0) sm[wposT] = v;
     }
   }
-  __syncwarp();
+  chain_sync<NW>(bar);
   int* meta = reinterpret_cast<int*>(sm + L.meta);
   int* wposv = reinterpret_cast<int*>(sm + L.wpos);
   int* wposTv = reinterpret_cast<int*>(sm + L.wposT);
-  for (int i = lane; i < (int)P.d; i += 32) {
+  for (int i = ct; i < (int)P.d; i += C::T) {
     const long long f = P.sens_ind ? __ldg(P.sens_ind + i) : (long long)i;
     int wpos, wposT, a, b;
     decode_coord(P, W, f, wpos, wposT, a, b);
@@ -254,62 +298,63 @@ __device__ float chain_init(float* sm, const SmallParams& P, const float* q_row,
     sm[wpos] = qv;
     if (wposT >= 0) sm[wposT] = qv;
   }
-  const float yv = stage_chunk<W>(sm, P, lane, 0);
-  __syncwarp();
+  const float yv = stage_chunk<W, NW>(sm, P, ct, 0);
+  chain_sync<NW>(bar);
   return yv;
 }
 
-// forward pass of the staged chunk; returns the network output of this lane's data point (point mode)
-template <int W>
-__device__ __forceinline__ float forward_chunk(float* sm, const SmallParams& P, int lane) {
-  constexpr int G = 32 / W, NC = G * 8, NCS = NC + 4, WSW = (W + 3) / 4 * 4;
+// forward pass of the staged chunk; returns the network output of this thread's data point (point mode)
+template <int W, int NW>
+__device__ __forceinline__ float forward_chunk(float* sm, const SmallParams& P, int ct, int bar) {
+  using C = Cfg<W, NW>;
+  constexpr int PPL = C::PPL, NCS = C::NCS, WSW = C::WSW;
   const SmallLayout& L = P.lay;
   float* act = sm + L.act_base;
-  const int j = lane % W, c0 = (lane / W) * 8;
-  const bool unit = lane < G * W;
+  const int j = ct % W, c0 = (ct / W) * PPL;
+  const bool unit = ct < C::G * W;
   if (unit) {  // layer 0: runtime input width
-    float z[8], da[8];
+    float z[PPL], da[PPL];
     const float b = sm[L.bbase[0] + j];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) z[t] = b;
+    for (int t = 0; t < PPL; ++t) z[t] = b;
     if (P.in_dim == 1) {  // the reference's nets: Linear(1, w0)
       const float w = sm[L.wbase[0] + j * L.ws[0]];
-      float r[8];
+      float r[PPL];
       load8(act + L.xs + c0, r);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) z[t] = fmaf(w, r[t], z[t]);
+      for (int t = 0; t < PPL; ++t) z[t] = fmaf(w, r[t], z[t]);
     } else {
 #pragma unroll 1
       for (int k = 0; k < P.in_dim; ++k) {
         const float w = sm[L.wbase[0] + j * L.ws[0] + k];
-        float r[8];
+        float r[PPL];
         load8(act + L.xs + k * NCS + c0, r);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) z[t] = fmaf(w, r[t], z[t]);
+        for (int t = 0; t < PPL; ++t) z[t] = fmaf(w, r[t], z[t]);
       }
     }
     activate8(P.act, z, da);
     store8(act + L.h + j * NCS + c0, z);
     if (P.act == VIHMC_ACT_SINE) store8(act + L.da + j * NCS + c0, da);
   }
-  __syncwarp();
+  chain_sync<NW>(bar);
   for (int l = 1; l < P.n_hidden; ++l) {
     if (unit) {
-      float z[8], da[8];
+      float z[PPL], da[PPL];
       const float b = sm[L.bbase[l] + j];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) z[t] = b;
+      for (int t = 0; t < PPL; ++t) z[t] = b;
       dot_rows<W, NCS>(sm + L.wbase[l] + j * WSW, act + L.h + (l - 1) * W * NCS + c0, z);
       activate8(P.act, z, da);
       store8(act + L.h + (l * W + j) * NCS + c0, z);
       if (P.act == VIHMC_ACT_SINE) store8(act + L.da + (l * W + j) * NCS + c0, da);
     }
-    __syncwarp();
+    chain_sync<NW>(bar);
   }
   float o = 0.0f;
-  if (lane < NC) {  // output layer, out_dim = 1
+  if (ct < C::NC) {  // output layer, out_dim = 1
     const float* wo = sm + L.wbase[P.n_hidden];
-    const float* hl = act + L.h + (P.n_hidden - 1) * W * NCS + lane;
+    const float* hl = act + L.h + (P.n_hidden - 1) * W * NCS + ct;
     o = sm[L.bbase[P.n_hidden]];
 #pragma unroll
     for (int k = 0; k < W; ++k) o = fmaf(wo[k], hl[k * NCS], o);
@@ -318,56 +363,57 @@ __device__ __forceinline__ float forward_chunk(float* sm, const SmallParams& P, 
 }
 
 // backward pass: writes the pre-activation gradients dz of every hidden layer (dO is already in smem)
-template <int W>
-__device__ __forceinline__ void backward_chunk(float* sm, const SmallParams& P, int lane) {
-  constexpr int G = 32 / W, NC = G * 8, NCS = NC + 4, WSW = (W + 3) / 4 * 4;
+template <int W, int NW>
+__device__ __forceinline__ void backward_chunk(float* sm, const SmallParams& P, int ct, int bar) {
+  using C = Cfg<W, NW>;
+  constexpr int PPL = C::PPL, NCS = C::NCS, WSW = C::WSW;
   const SmallLayout& L = P.lay;
   float* act = sm + L.act_base;
-  const int j = lane % W, c0 = (lane / W) * 8;
-  const bool unit = lane < G * W;
+  const int j = ct % W, c0 = (ct / W) * PPL;
+  const bool unit = ct < C::G * W;
   const int top = P.n_hidden - 1;
   if (unit) {
-    float dO[8], da[8], dz[8];
+    float dO[PPL], da[PPL], dz[PPL];
     const float wo = sm[L.wbase[P.n_hidden] + j];
     load8(act + L.dO + c0, dO);
     load_dact8(P.act, act + L.h + (top * W + j) * NCS + c0, act + L.da + (top * W + j) * NCS + c0, da);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) dz[t] = wo * dO[t] * da[t];
+    for (int t = 0; t < PPL; ++t) dz[t] = wo * dO[t] * da[t];
     store8(act + L.dz + (top * W + j) * NCS + c0, dz);
   }
-  __syncwarp();
+  chain_sync<NW>(bar);
   for (int l = top; l >= 1; --l) {
     if (unit) {
-      float acc[8], da[8];
+      float acc[PPL], da[PPL];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
+      for (int t = 0; t < PPL; ++t) acc[t] = 0.0f;
       dot_rows<W, NCS>(sm + L.tbase[l] + j * WSW, act + L.dz + l * W * NCS + c0, acc);
       load_dact8(P.act, act + L.h + ((l - 1) * W + j) * NCS + c0, act + L.da + ((l - 1) * W + j) * NCS + c0, da);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[t] *= da[t];
+      for (int t = 0; t < PPL; ++t) acc[t] *= da[t];
       store8(act + L.dz + ((l - 1) * W + j) * NCS + c0, acc);
     }
-    __syncwarp();
+    chain_sync<NW>(bar);
   }
 }
 
-// phase B: lane = sampled coordinate; accumulates d loglik / d q_i of the staged chunk.  On the last
+// phase B: thread = sampled coordinate; accumulates d loglik / d q_i of the staged chunk.  On the last
 // chunk the finished likelihood gradient of coordinate i goes straight to `consume(i, g_i)` (prior, kick,
 // drift, weight-table scatter: one pass, no round trip through sm[g]); earlier chunks park it in sm[g].
-template <int W, typename Consume>
-__device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int lane, bool first_chunk, bool last_chunk,
+template <int W, int NW, typename Consume>
+__device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int ct, bool first_chunk, bool last_chunk,
                                         Consume&& consume) {
-  constexpr int NC = (32 / W) * 8;
+  using C = Cfg<W, NW>;
   const SmallLayout& L = P.lay;
   const float* act = sm + L.act_base;
   const int* meta = reinterpret_cast<const int*>(sm + L.meta);
-  for (int i = lane; i < (int)P.d; i += 32) {
+  for (int i = ct; i < (int)P.d; i += C::T) {
     const int m = meta[i];
     const float4* A = reinterpret_cast<const float4*>(act + (m >> 16));
     const float4* B = reinterpret_cast<const float4*>(act + (m & 0xffff));
     float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
 #pragma unroll
-    for (int c = 0; c < NC / 4; ++c) {
+    for (int c = 0; c < C::NC / 4; ++c) {
       const float4 a = A[c], b = B[c];
       acc0 = fmaf(a.x, b.x, acc0);
       acc1 = fmaf(a.y, b.y, acc1);
@@ -382,32 +428,32 @@ __device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int lan
 }
 
 // One gradient evaluation: consume(i, d loglik / d q_i) is called once per sampled coordinate (no prior
-// yet); returns this lane's share of the log-likelihood.  yv0 = the lane's target when N fits one chunk.
-template <int W, typename Consume>
-__device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallParams& P, const Likelihood lik, int lane, float yv0,
-                                                      Consume&& consume) {
-  constexpr int NC = (32 / W) * 8;
+// yet); returns this thread's share of the log-likelihood.  yv0 = the thread's target when N fits one chunk.
+template <int W, int NW, typename Consume>
+__device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallParams& P, const Likelihood lik, int ct, int bar,
+                                                      float yv0, Consume&& consume) {
+  using C = Cfg<W, NW>;
   const SmallLayout& L = P.lay;
   float* act = sm + L.act_base;
-  const int n_chunks = (int)((P.N + NC - 1) / NC);
+  const int n_chunks = (int)((P.N + C::NC - 1) / C::NC);
   float ll_lane = 0.0f;
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     float yv = yv0;
     if (n_chunks > 1) {
-      yv = stage_chunk<W>(sm, P, lane, chunk);
-      __syncwarp();
+      yv = stage_chunk<W, NW>(sm, P, ct, chunk);
+      chain_sync<NW>(bar);
     }
-    const float o = forward_chunk<W>(sm, P, lane);
-    if (lane < NC) {
-      const bool valid = (long long)chunk * NC + lane < P.N;
+    const float o = forward_chunk<W, NW>(sm, P, ct, bar);
+    if (ct < C::NC) {
+      const bool valid = (long long)chunk * C::NC + ct < P.N;
       const float r = o - yv;
-      act[L.dO + lane] = valid ? -lik.prec * r : 0.0f;
+      act[L.dO + ct] = valid ? -lik.prec * r : 0.0f;
       if (valid) ll_lane += lik.ll_const - lik.half_prec * r * r;
     }
-    __syncwarp();
-    backward_chunk<W>(sm, P, lane);
-    phase_b<W>(sm, P, lane, chunk == 0, chunk == n_chunks - 1, consume);
-    __syncwarp();
+    chain_sync<NW>(bar);
+    backward_chunk<W, NW>(sm, P, ct, bar);
+    phase_b<W, NW>(sm, P, ct, chunk == 0, chunk == n_chunks - 1, consume);
+    chain_sync<NW>(bar);
   }
   return ll_lane;
 }
@@ -415,50 +461,54 @@ __device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallPara
 // ------------------------------------------------------------------------------------------------
 // kernel 1: log-posterior value + gradient for C chains (vihmc_logp_grad, MLP small path)
 // ------------------------------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C, const float* __restrict__ q,
-                                                                  float* __restrict__ logp, float* __restrict__ grad) {
+template <int W, int NW>
+__global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C,
+                                                                                         const float* __restrict__ q,
+                                                                                         float* __restrict__ logp,
+                                                                                         float* __restrict__ grad) {
   extern __shared__ __align__(16) float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long chain = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  constexpr int T = Cfg<W, NW>::T;
+  const int ct = threadIdx.x % T, slot = threadIdx.x / T, bar = 1 + slot;
+  const long long chain = (long long)blockIdx.x * (blockDim.x / T) + slot;
   if (chain >= C) return;
   const SmallLayout& L = P.lay;
-  float* sm = smem + (size_t)warp * L.total;
-  const float yv0 = chain_init<W>(sm, P, q + chain * P.d, lane);
+  float* sm = smem + (size_t)slot * L.total;
+  const float yv0 = chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
   float lp_lane = 0.0f;
-  const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0, [&](int i, float gl) {
+  const float ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, [&](int i, float gl) {
     const float dq = sm[L.q + i] - sm[L.pmu + i], iv = sm[L.piv + i];
     lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
     if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, gl);
   });
-  const float total = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + P.prior_log_norm * P.inv_prior_scale;
-  if (lane == 0) logp[chain] = total;
+  const float total = chain_sum<NW>(fmaf(lp_lane, P.inv_prior_scale, ll_lane), sm + L.red, ct, bar) + P.prior_log_norm * P.inv_prior_scale;
+  if (ct == 0) logp[chain] = total;
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel 1b: forward only (vihmc_predict, MLP small path): out[C, N]
 // ------------------------------------------------------------------------------------------------
-template <int W>
+template <int W, int NW>
 __global__ void __launch_bounds__(128) mlp_small_predict_kernel(SmallParams P, long long C, const float* __restrict__ q,
                                                                 float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int NC = (32 / W) * 8;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long chain = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  using Cf = Cfg<W, NW>;
+  constexpr int T = Cf::T;
+  const int ct = threadIdx.x % T, slot = threadIdx.x / T, bar = 1 + slot;
+  const long long chain = (long long)blockIdx.x * (blockDim.x / T) + slot;
   if (chain >= C) return;
-  float* sm = smem + (size_t)warp * P.lay.total;
-  chain_init<W>(sm, P, q + chain * P.d, lane);
-  const int n_chunks = (int)((P.N + NC - 1) / NC);
+  float* sm = smem + (size_t)slot * P.lay.total;
+  chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar);
+  const int n_chunks = (int)((P.N + Cf::NC - 1) / Cf::NC);
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     if (chunk > 0) {
-      stage_chunk<W>(sm, P, lane, chunk);
-      __syncwarp();
+      stage_chunk<W, NW>(sm, P, ct, chunk);
+      chain_sync<NW>(bar);
     }
-    const float o = forward_chunk<W>(sm, P, lane);
-    const long long n = (long long)chunk * NC + lane;
-    if (lane < NC && n < P.N) out[chain * P.N + n] = o;
-    __syncwarp();
+    const float o = forward_chunk<W, NW>(sm, P, ct, bar);
+    const long long n = (long long)chunk * Cf::NC + ct;
+    if (ct < Cf::NC && n < P.N) out[chain * P.N + n] = o;
+    chain_sync<NW>(bar);
   }
 }
 
@@ -478,18 +528,20 @@ struct SampleArgs {
   const float* inj_u;
 };
 
-template <int W>
+template <int W, int NW>
 __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
   extern __shared__ __align__(16) float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long chain = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  constexpr int T = Cfg<W, NW>::T;
+  const int ct = threadIdx.x % T, slot = threadIdx.x / T, bar = 1 + slot;
+  const long long chain = (long long)blockIdx.x * (blockDim.x / T) + slot;
   if (chain >= A.C) return;
   const SmallLayout& L = P.lay;
-  float* sm = smem + (size_t)warp * L.total;
+  float* sm = smem + (size_t)slot * L.total;
+  float* red = sm + L.red;
   const int d = (int)P.d;
   const long long C = A.C;
   const float* q0 = A.q0 + chain * d;
-  const float yv0 = chain_init<W>(sm, P, q0, lane);
+  const float yv0 = chain_init<W, NW>(sm, P, q0, ct, bar);
   const int* wposv = reinterpret_cast<const int*>(sm + L.wpos);
   const int* wposTv = reinterpret_cast<const int*>(sm + L.wposT);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
@@ -497,30 +549,30 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
   const int S = A.cfg.num_samples, nsteps = A.cfg.num_steps, burn = A.cfg.burn;
   const float log_norm = P.prior_log_norm * P.inv_prior_scale;
 
-  // dual-averaging state (Sampler.HMC_NUTS): every lane carries the same scalars
+  // dual-averaging state (Sampler.HMC_NUTS): every thread of the chain carries the same scalars
   float eps = A.cfg.step_size;
   const float eps_init = A.cfg.step_size;
   float eps_bar = 1.0f, H_t = 0.0f;
 
-  for (int i = lane; i < d; i += 32) A.samples[chain * d + i] = sm[L.q + i];  // stored row 0 = params_init
+  for (int i = ct; i < d; i += T) A.samples[chain * d + i] = sm[L.q + i];  // stored row 0 = params_init
   float logp_init = 0.0f, logp_f = 0.0f;  // log-posterior of params_init / of the fallback state
 
   for (int n = 0; n < S; ++n) {
     if (A.cfg.hamiltorch_fallback_rule && n == burn + 1) {
-      for (int i = lane; i < d; i += 32) sm[L.qf + i] = q0[i];
+      for (int i = ct; i < d; i += T) sm[L.qf + i] = q0[i];
       logp_f = logp_init;
     }
     // ---- momentum ----
     float ke = 0.0f;
     if (A.inj_p != nullptr) {
       const float* src = A.inj_p + ((long long)n * C + chain) * d;
-      for (int i = lane; i < d; i += 32) {
+      for (int i = ct; i < d; i += T) {
         const float pv = src[i];
         sm[L.p + i] = pv;
         ke = fmaf(pv, pv, ke);
       }
     } else {
-      for (int jb = lane; 4 * jb < d; jb += 32) {
+      for (int jb = ct; 4 * jb < d; jb += T) {
         const float4 z = philox_normal4(A.cfg.seed, gchain, (uint32_t)n, (uint32_t)jb, STREAM_MOMENTUM);
         const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -531,8 +583,8 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
           }
       }
     }
-    const float ke0 = 0.5f * warp_sum(ke);
-    __syncwarp();
+    const float ke0 = 0.5f * chain_sum<NW>(ke, red, ct, bar);
+    chain_sync<NW>(bar);
 
     // ---- trajectory: evaluation s = 0 yields H0 and the first half kick; s = nsteps yields H1 ----
     const float half_eps = 0.5f * eps;
@@ -541,7 +593,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
       const bool first = s == 0, last = s == nsteps;
       const float kick = first ? half_eps : eps;
       float lp_lane = 0.0f, ke_lane = 0.0f;
-      const float ll_lane = eval_likelihood_grad<W>(sm, P, lik, lane, yv0, [&](int i, float gl) {
+      const float ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, [&](int i, float gl) {
         const float qv0 = sm[L.q + i];
         const float dq = qv0 - sm[L.pmu + i], iv = sm[L.piv + i];
         lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
@@ -561,17 +613,17 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
         sm[L.p + i] = pv;
       });
       if (first || last) {
-        const float lp = warp_sum(fmaf(lp_lane, P.inv_prior_scale, ll_lane)) + log_norm;
+        const float lp = chain_sum<NW>(fmaf(lp_lane, P.inv_prior_scale, ll_lane), red, ct, bar) + log_norm;
         if (first) logp0 = lp;
-        if (last) { logp1 = lp; ke1 = 0.5f * warp_sum(ke_lane); }
+        if (last) { logp1 = lp; ke1 = 0.5f * chain_sum<NW>(ke_lane, red, ct, bar); }
       }
-      __syncwarp();
+      chain_sync<NW>(bar);
     }
     const float H0 = -logp0 + ke0, H1 = -logp1 + ke1;
     if (n == 0) {
       logp_init = logp0;
       logp_f = logp0;
-      if (A.logp_out != nullptr && lane == 0) A.logp_out[chain] = logp0;
+      if (A.logp_out != nullptr && ct == 0) A.logp_out[chain] = logp0;
     }
     // ---- Metropolis test (hamiltorch: rho = min(0, H0-H1); accept iff rho >= log u) ----
     const float u = A.inj_u != nullptr ? A.inj_u[(long long)n * C + chain] : philox_uniform(A.cfg.seed, gchain, (uint32_t)n);
@@ -582,13 +634,13 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
     float* row = store ? A.samples + ((long long)(n - burn) * C + chain) * d : nullptr;
     if (accept) {
       logp_f = logp1;
-      for (int i = lane; i < d; i += 32) {
+      for (int i = ct; i < d; i += T) {
         const float qv = sm[L.q + i];
         sm[L.qf + i] = qv;
         if (store) row[i] = qv;
       }
     } else {
-      for (int i = lane; i < d; i += 32) {
+      for (int i = ct; i < d; i += T) {
         const float qv = sm[L.qf + i];
         sm[L.q + i] = qv;
         sm[wposv[i]] = qv;
@@ -597,7 +649,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
         if (store) row[i] = qv;
       }
     }
-    if (lane == 0) {
+    if (ct == 0) {
       if (A.accepted != nullptr) A.accepted[(long long)n * C + chain] = accept ? 1 : 0;
       if (A.hamiltonians != nullptr) {
         A.hamiltonians[((long long)n * C + chain) * 2 + 0] = H0;
@@ -619,9 +671,9 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
       }
       if (n == burn) eps = eps_bar;
     }
-    __syncwarp();
+    chain_sync<NW>(bar);
   }
-  if (A.step_sizes != nullptr && lane == 0) A.step_sizes[chain] = eps;
+  if (A.step_sizes != nullptr && ct == 0) A.step_sizes[chain] = eps;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,7 +682,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
 enum SmallOp { kOpLogpGrad = 0, kOpPredict = 1, kOpSample = 2 };
 
 struct SmallLaunch {
-  int warps_per_block, blocks;
+  int warps_per_chain, chains_per_block, blocks;
   size_t smem;
   long long C;
   const float* q;
@@ -646,26 +698,32 @@ static int set_smem(K kernel, size_t bytes) {
   return VIHMC_OK;
 }
 
-template <int W>
-static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
-  const int threads = a.warps_per_block * 32;
+template <int W, int NW>
+static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
+  const int threads = a.chains_per_block * 32 * NW;
   if (op == kOpLogpGrad) {
-    auto k = mlp_small_logp_grad_kernel<W>;
+    auto k = mlp_small_logp_grad_kernel<W, NW>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.logp, a.grad);
     VIHMC_LAUNCH_OK("mlp_small_logp_grad_kernel");
   } else if (op == kOpPredict) {
-    auto k = mlp_small_predict_kernel<W>;
+    auto k = mlp_small_predict_kernel<W, NW>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.out);
     VIHMC_LAUNCH_OK("mlp_small_predict_kernel");
   } else {
-    auto k = mlp_small_sample_kernel<W>;
+    auto k = mlp_small_sample_kernel<W, NW>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.A);
     VIHMC_LAUNCH_OK("mlp_small_sample_kernel");
   }
   return VIHMC_OK;
+}
+
+template <int W>
+static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
+  if (a.warps_per_chain == 2) return launch_small_wn<W, 2>(op, P, a, st);
+  return launch_small_wn<W, 1>(op, P, a, st);
 }
 
 }  // namespace vihmc
