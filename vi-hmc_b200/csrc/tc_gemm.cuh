@@ -8,19 +8,22 @@
 // shared memory as exact tf32 values, low 13 mantissa bits zero, so the result does not depend on how the
 // tensor core converts fp32 bits to tf32) and the product is hi*hi + lo*hi + hi*lo, accumulated in fp32.
 //
-// Structure of one CTA (256 threads, one 128 x 128 output tile, 64 KB smem, 256 TMEM columns => 2 CTAs / SM so one CTA's
+// Structure of one CTA (256 threads, one 128 x 128 output tile, 3 x 32 KB smem stages, 256 TMEM columns => exactly
+// 2 CTAs / SM, so no third CTA sits spinning in tcgen05.alloc so one CTA's
 // epilogue overlaps another's main loop):
 //   * all 8 warps stream the A / B k-tiles (16 floats deep) from global memory through registers, split
 //     them, and store hi/lo tiles in the UMMA canonical K-major no-swizzle layout (8x16B core matrices);
 //     arbitrary element strides are supported, so transposed operands (dW = dZ^T X, dX = dZ W) and
 //     rows that are not 16-byte aligned (101-wide branch input) need no extra copies -- this is also
 //     why the operands are not staged with TMA: the split needs the values in registers anyway.
-//   * two smem stages; thread 0 issues 3 MMAs per 8-deep k-step and commits to the stage's mbarrier;
+//   * three smem stages; thread 0 issues 3 MMAs per 8-deep k-step and commits to the stage's mbarrier;
 //     the next tile's global loads are in flight while the tensor core works.
 //   * epilogue: 8 warps read the accumulators with tcgen05.ld (warp w -> TMEM lanes 32*(w%4).., column
 //     half w/4) into a shared-memory tile, then apply bias+act / act' / Gaussian residual and write C
 //     row-wise so every warp instruction touches contiguous memory.
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vihmc {
@@ -51,7 +54,7 @@ struct GemmArgs {
 
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256, STAGES = 2;
+constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256, STAGES = 3;
 constexpr int CHUNKS = BK / 4;                 // 16-byte chunks along K per row
 constexpr int LBO = 128;                       // bytes between the K-chunks of a core-matrix row group
 constexpr int SBO = CHUNKS * 128;              // bytes between 8-row groups
@@ -161,6 +164,61 @@ __device__ __forceinline__ void stash(unsigned char* hi_tile, unsigned char* lo_
   }
 }
 
+
+// Phase-2 epilogue of one staged row: applies the fused epilogue to tile_row[0..BN) and writes C.  With `vec`
+// (C rows 16-byte aligned, N % 4 == 0) every lane handles 4 consecutive columns with one LDS.128 / STG.128
+// (one warp instruction = one 512-byte row); otherwise lane + 32*j columns (128 contiguous bytes each).
+template <int EPI>
+__device__ __forceinline__ void epilogue_row(const GemmArgs& g, const float* tile_row, float* crow, const float* arow,
+                                             const float* biasb, int n0, int lane, bool vec, bool vec_aux, float bias0,
+                                             float& ll_acc, float& g_acc) {
+  auto apply = [&](float v, float bias_v, float aux_v) -> float {
+    if (EPI == EPI_BIAS_ACT) {
+      v += bias_v;
+      if (g.act == VIHMC_ACT_TANH) v = tanh_sel(v);   // 8 instructions, abs. error ~1.2e-7 (see common.cuh)
+      else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+    } else if (EPI == EPI_DACT) {
+      v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - aux_v * aux_v) : (aux_v > 0.0f ? 1.0f : 0.0f);
+    } else if (EPI == EPI_HEAD) {
+      const float res = v + bias0 - aux_v;
+      ll_acc += g.ll_const - g.half_prec * res * res;
+      v = -g.prec * res;
+      g_acc += v;
+    }
+    return v;
+  };
+  if (vec) {
+    const int c = lane * 4;
+    if (n0 + c < g.N) {   // N % 4 == 0: the whole float4 is in range
+      const float4 v = *reinterpret_cast<const float4*>(tile_row + c);
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI == EPI_BIAS_ACT) {
+        bv.x = __ldg(biasb + n0 + c); bv.y = __ldg(biasb + n0 + c + 1); bv.z = __ldg(biasb + n0 + c + 2); bv.w = __ldg(biasb + n0 + c + 3);
+      }
+      if (EPI == EPI_DACT || EPI == EPI_HEAD) {
+        if (vec_aux) av = __ldg(reinterpret_cast<const float4*>(arow + c));
+        else { av.x = __ldg(arow + c); av.y = __ldg(arow + c + 1); av.z = __ldg(arow + c + 2); av.w = __ldg(arow + c + 3); }
+      }
+      float4 o;
+      o.x = apply(v.x, bv.x, av.x); o.y = apply(v.y, bv.y, av.y); o.z = apply(v.z, bv.z, av.z); o.w = apply(v.w, bv.w, av.w);
+      *reinterpret_cast<float4*>(crow + c) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      if (n0 + c >= g.N) continue;
+      const float bias_v = (EPI == EPI_BIAS_ACT) ? __ldg(biasb + n0 + c) : 0.0f;
+      const float aux_v = (EPI == EPI_DACT || EPI == EPI_HEAD) ? __ldg(arow + c) : 0.0f;
+      crow[c] = apply(tile_row[c], bias_v, aux_v);
+    }
+  }
+}
+
+__device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, long long ld, int N) {
+  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && bs % 4 == 0 && ld % 4 == 0 && N % 4 == 0;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_vec, int b_vec) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -183,8 +241,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   }
 
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&mbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -204,9 +261,9 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   la.fetch(0, tid, ra);
   lb.fetch(0, tid, rb);
   for (int kt = 0; kt < nk; ++kt) {
-    const int s = kt & 1;
+    const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
-    if (kt >= 2) mbar_wait(&mbar[s], (uint32_t)((kt >> 1) - 1) & 1u);   // the MMAs that read this stage are done
+    if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
     stash(st, st + TILE_BYTES, tid, ra);
     stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, rb);
     if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
@@ -236,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
       mma_commit(&mbar[s]);
     }
   }
-  mbar_wait(&mbar[(nk - 1) & 1], (uint32_t)((nk - 1) >> 1) & 1u);   // commits complete in order: everything is done
+  mbar_wait(&mbar[(nk - 1) % STAGES], (uint32_t)((nk - 1) / STAGES) & 1u);   // commits complete in order: everything is done
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---------------- epilogue ----------------
@@ -270,40 +327,15 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)b * g.bias_bs) : 0.0f;
   const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs : nullptr;
   const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
+  const bool vec = rows_vec_ok(g.C, g.c_bs, g.ldc, g.N);
+  const bool vec_aux = auxb != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N);
   float ll_acc = 0.0f, g_acc = 0.0f;
-  float bias_r[4] = {0.f, 0.f, 0.f, 0.f};   // this lane's four columns: loaded once, not once per row
-  if (EPI == EPI_BIAS_ACT) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (n0 + lane + 32 * j < g.N) bias_r[j] = __ldg(biasb + n0 + lane + 32 * j);
-  }
-#pragma unroll 1
+#pragma unroll 2
   for (int r = warp; r < BM; r += THREADS / 32) {
     const int m = m0 + r;
     if (m >= g.M) break;
-    float* crow = Cb + (long long)m * g.ldc + n0;
-    const float* arow = auxb ? auxb + (long long)m * g.ld_aux + n0 : nullptr;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = lane + 32 * j;           // 128 contiguous bytes per warp instruction
-      const int n = n0 + c;
-      if (n >= g.N) continue;
-      float v = tile[r * TILE_LD + c];
-      if (EPI == EPI_BIAS_ACT) {
-        v += bias_r[j];
-        if (g.act == VIHMC_ACT_TANH) v = tanh_sel(v);   // 8 instructions, abs. error ~1.2e-7 (see common.cuh)
-        else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
-      } else if (EPI == EPI_DACT) {
-        const float a = __ldg(arow + c);
-        v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - a * a) : (a > 0.0f ? 1.0f : 0.0f);
-      } else if (EPI == EPI_HEAD) {
-        const float res = v + bias0 - __ldg(arow + c);
-        ll_acc += g.ll_const - g.half_prec * res * res;
-        v = -g.prec * res;
-        g_acc += v;
-      }
-      crow[c] = v;
-    }
+    epilogue_row<EPI>(g, tile + r * TILE_LD, Cb + (long long)m * g.ldc + n0, auxb ? auxb + (long long)m * g.ld_aux + n0 : nullptr,
+                      biasb, n0, lane, vec, vec_aux, bias0, ll_acc, g_acc);
   }
   if (EPI == EPI_HEAD) {
     float* red = reinterpret_cast<float*>(smem);
@@ -327,6 +359,233 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
 }
 
 }  // namespace tc
+
+// =============================================================================================
+// Persistent, warp-specialised variant (opt-in, VIHMC_TC_PERSISTENT=1): one CTA per SM loops over output tiles.
+//   warps 0-7   producers: global -> registers -> 3xTF32 split -> shared-memory stage (4-stage ring, full/empty
+//               mbarriers), running ahead of the tensor core by up to four k-tiles, across tile boundaries;
+//   warp  8     MMA issuer: waits full[s], issues the three tcgen05.mma of each k-step into accumulator set
+//               a = tile & 1 (TMEM columns a*256 .. a*256+255: main + correction), tcgen05.commit -> empty[s];
+//               after the last k-tile tcgen05.commit -> tmem_full[a];
+//   warps 9-16  epilogue (two per TMEM lane quarter, 64 columns each): wait tmem_full[a], tcgen05.ld the 128x128 accumulators into a shared staging tile,
+//               release the accumulator set (tmem_empty[a]) so the MMAs of tile i+2 can start, then the
+//               row-wise coalesced epilogue of tile i runs while the tensor core works on tile i+1.
+// Compared with the one-tile-per-CTA kernel this removes the per-tile TMEM allocation / barrier setup and
+// overlaps epilogue and main loop inside one SM (K = 100 layers have only 7 k-tiles per tile).
+// =============================================================================================
+namespace tcws {
+
+using namespace tc;
+constexpr int WS_STAGES = 4;
+constexpr int PRODUCER_WARPS = 8, EPI_WARPS = 8;
+constexpr int WS_THREADS = (PRODUCER_WARPS + 1 + EPI_WARPS) * 32;   // 544
+constexpr int WS_EPI_OFF = WS_STAGES * STAGE_BYTES;                  // 128 KB of operand stages
+constexpr int WS_BAR_OFF = WS_EPI_OFF + EPI_BYTES;                   // + 67,584 B staging tile
+constexpr int WS_SMEM_BYTES = WS_BAR_OFF + 256;
+constexpr int EPI_BAR_ID = 1;                                        // named barrier of the 128 epilogue threads
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR_ID), "n"(EPI_WARPS * 32) : "memory"); }
+
+struct TileCoord {
+  int b, m0, n0, K;
+  const float *A, *B;
+  float* C;
+  long long c_bs, ldc;
+  long long tile_linear;   // index into the per-batch partial arrays (EPI_HEAD)
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, long long t, int tiles_n, int tiles_m) {
+  TileCoord tc;
+  const int bx = (int)(t % tiles_n), by = (int)((t / tiles_n) % tiles_m), bz = (int)(t / ((long long)tiles_n * tiles_m));
+  const bool split = g.splits > 1;
+  tc.b = split ? bz / g.splits : bz;
+  const int ks = split ? bz % g.splits : 0;
+  tc.m0 = by * BM;
+  tc.n0 = bx * BN;
+  tc.A = g.A + (long long)tc.b * g.a_bs;
+  tc.B = g.B + (long long)tc.b * g.b_bs;
+  tc.K = g.K;
+  tc.C = g.C + (long long)tc.b * g.c_bs;
+  tc.c_bs = g.c_bs;
+  tc.ldc = g.ldc;
+  if (split) {
+    const int k_lo = ks * g.kc;
+    tc.A += (long long)k_lo * g.a_sk;
+    tc.B += (long long)k_lo * g.b_sk;
+    tc.K = (g.K - k_lo) < g.kc ? (g.K - k_lo) : g.kc;
+    tc.C = g.split_buf + ((long long)ks * g.batch + tc.b) * (long long)g.M * g.N;
+    tc.ldc = g.N;
+  }
+  tc.tile_linear = (long long)by * tiles_n + bx;
+  return tc;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(GemmArgs g, int a_vec, int b_vec, int tiles_n, int tiles_m,
+                                                                   long long total_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WS_BAR_OFF);          // [WS_STAGES]
+  uint64_t* empty = full + WS_STAGES;                                       // [WS_STAGES]
+  uint64_t* tmem_full = empty + WS_STAGES;                                  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);                     // [2 * EPI_WARPS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) {
+      mbar_init(&full[s], PRODUCER_WARPS);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PRODUCER_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < PRODUCER_WARPS) {
+    // ===================== producers =====================
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(g, t, tiles_n, tiles_m);
+      TileLoader la{tc.A, g.a_sm, g.a_sk, g.M, tc.K, tc.m0, a_vec != 0};
+      TileLoader lb{tc.B, g.b_sn, g.b_sk, g.N, tc.K, tc.n0, b_vec != 0};
+      const int nk = (tc.K + BK - 1) / BK;
+      float4 ra[2], rb[2];
+      la.fetch(0, tid, ra);
+      lb.fetch(0, tid, rb);
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1u;
+        unsigned char* st = smem + s * STAGE_BYTES;
+        mbar_wait(&empty[s], ph ^ 1u);
+        stash(st, st + TILE_BYTES, tid, ra);
+        stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, rb);
+        if (kt + 1 < nk) {
+          la.fetch((kt + 1) * BK, tid, ra);
+          lb.fetch((kt + 1) * BK, tid, rb);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == PRODUCER_WARPS) {
+    // ===================== MMA issuer =====================
+    uint32_t it = 0, tcount = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(g, t, tiles_n, tiles_m);
+      const int nk = (tc.K + BK - 1) / BK;
+      const uint32_t a = tcount & 1u;
+      mbar_wait(&tmem_empty[a], ((tcount >> 1) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem_base + a * 256u, d_corr = d_main + (uint32_t)BN;
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const int steps = (tc.K - kt * BK) > 8 ? 2 : 1;
+          for (int ks = 0; ks < steps; ++ks) {
+            const uint32_t koff = (uint32_t)ks * 2u * LBO;
+            const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa + TILE_BYTES + koff);
+            const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES + koff), b_lo = make_desc(sa + 3 * TILE_BYTES + koff);
+            const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
+            mma_tf32(d_main, a_hi, b_hi, acc);
+            mma_tf32(d_corr, a_lo, b_hi, acc);
+            mma_tf32(d_corr, a_hi, b_lo, 1u);
+          }
+          mma_commit(&empty[s]);                       // stage reusable once these MMAs have read it
+          if (kt == nk - 1) mma_commit(&tmem_full[a]); // accumulators of this tile complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int e = warp - PRODUCER_WARPS - 1;          // 0..7
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int half = e >> 2;                          // which 64 accumulator columns this warp drains
+    float* tile = reinterpret_cast<float*>(smem + WS_EPI_OFF);
+    uint32_t tcount = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(g, t, tiles_n, tiles_m);
+      const uint32_t a = tcount & 1u;
+      mbar_wait(&tmem_full[a], (tcount >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // phase 1: TMEM -> staging tile (thread = accumulator row q*32+lane, 64 columns)
+      {
+        float* trow = tile + (q * 32 + lane) * TILE_LD + half * (BN / 2);
+        const uint32_t tbase = tmem_base + a * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+#pragma unroll 2
+        for (int cc = 0; cc < BN / 2; cc += 8) {
+          uint32_t r[8], rc[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                       : "r"(tbase + (uint32_t)cc));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
+                       : "r"(tbase + (uint32_t)(BN + cc)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+          *reinterpret_cast<float4*>(trow + cc) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(trow + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      epi_bar();                                       // tile staged, every TMEM read of this set retired
+      if (e == 0 && lane == 0) mbar_arrive(&tmem_empty[a]);
+      // phase 2: row-wise coalesced epilogue
+      const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)tc.b * g.bias_bs) : 0.0f;
+      const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)tc.b * g.aux_bs : nullptr;
+      const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)tc.b * g.bias_bs : nullptr;
+      const bool vec = rows_vec_ok(tc.C, tc.c_bs, tc.ldc, g.N) && (tc.n0 % 4 == 0);
+      const bool vec_aux = auxb != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N);
+      float ll_acc = 0.0f, g_acc = 0.0f;
+#pragma unroll 2
+      for (int r = e; r < BM; r += EPI_WARPS) {
+        const int m = tc.m0 + r;
+        if (m >= g.M) break;
+        epilogue_row<EPI>(g, tile + r * TILE_LD, tc.C + (long long)m * tc.ldc + tc.n0,
+                          auxb ? auxb + (long long)m * g.ld_aux + tc.n0 : nullptr, biasb, tc.n0, lane, vec, vec_aux, bias0, ll_acc,
+                          g_acc);
+      }
+      if (EPI == EPI_HEAD) {
+        ll_acc = warp_sum(ll_acc);
+        g_acc = warp_sum(g_acc);
+        if (lane == 0) { red[e] = ll_acc; red[EPI_WARPS + e] = g_acc; }
+      }
+      epi_bar();                                       // staging tile free for the next tile; partial sums visible
+      if (EPI == EPI_HEAD && e == 0 && lane == 0) {
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int w = 0; w < EPI_WARPS; ++w) { s0 += red[w]; s1 += red[EPI_WARPS + w]; }
+        const long long tiles = (long long)tiles_n * tiles_m;
+        g.part_ll[(long long)tc.b * tiles + tc.tile_linear] = s0;
+        g.part_g[(long long)tc.b * tiles + tc.tile_linear] = s1;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == PRODUCER_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+}  // namespace tcws
 
 // C[b, m, n] = sum_s split_buf[s, b, m, n] in fixed order (fp32 round-to-nearest adds)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ buf, int splits, int batch, int M, int N,
@@ -374,9 +633,36 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     g.split_buf = scratch;
     if ((long long)batch * g.splits > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch * splits > 65535");
   }
-  dim3 grid((g.N + tc::BN - 1) / tc::BN, (g.M + tc::BM - 1) / tc::BM, batch * g.splits);
-  k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_vec, b_vec);
-  VIHMC_LAUNCH_OK("tc_gemm_kernel");
+  // The persistent warp-specialised kernel (tcws) is opt-in: measured 21.4 ms vs 18.6 ms per 64-chain DeepONet
+  // gradient batch -- with K = 100 the epilogue is as heavy as the main loop, and 8 of 17 warps doing it lose to
+  // 16 warps (2 CTAs) that all take part in every phase.
+  static const bool simple = []() {
+    const char* e = getenv("VIHMC_TC_PERSISTENT");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  const int tiles_n = (g.N + tc::BN - 1) / tc::BN, tiles_m = (g.M + tc::BM - 1) / tc::BM;
+  if (simple) {
+    dim3 grid(tiles_n, tiles_m, batch * g.splits);
+    k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_vec, b_vec);
+    VIHMC_LAUNCH_OK("tc_gemm_kernel");
+  } else {
+    auto kw = tcws::tc_gemm_ws_kernel<EPI>;
+    static bool configured_ws = false;
+    if (!configured_ws) {
+      VIHMC_CUDA_OK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, tcws::WS_SMEM_BYTES));
+      configured_ws = true;
+    }
+    const long long total = (long long)tiles_n * tiles_m * batch * g.splits;
+    static const int num_sms = []() {
+      int dev = 0, n = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      return n;
+    }();
+    const int grid = (int)(total < num_sms ? total : num_sms);   // persistent: one CTA per SM
+    kw<<<grid, tcws::WS_THREADS, tcws::WS_SMEM_BYTES, st>>>(g, a_vec, b_vec, tiles_n, tiles_m, total);
+    VIHMC_LAUNCH_OK("tc_gemm_ws_kernel");
+  }
   if (g.splits > 1) {
     const long long total = (long long)batch * g.M * g.N;
     long long blocks = (total + 255) / 256;
