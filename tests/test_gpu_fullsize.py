@@ -1,0 +1,100 @@
+"""GPU tests at BASELINE.json's FULL sizes, through size-independent properties (the CPU oracle cannot run these
+sizes in seconds): determinism, sharding invariance, additivity of the split closures, the VI gather identity
+(grad_q == grad_W[sens_ind], my_make_func.py:56-57) and linearity of the prior in prior_scale."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from vihmc import engine, synth
+from vihmc.spec import DeepONetArch, LogProbSpec, sliced_prior_sigma
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg2():
+    x, y, _, _ = synth.bnn_data()
+    arch = synth.bnn_arch()
+    mu, sigma, ind = synth.bnn_vi_artifacts(arch.num_params, 40, seed=1)
+    sig = sliced_prior_sigma(40, arch.tensor_numels(), [1.0] * 6)
+    spec = LogProbSpec(arch=arch, x=x, y=y, loss="NLL", tau_out=0.0025, prior_sigma=torch.from_numpy(sig.astype(np.float32)),
+                       frozen=mu, sens_ind=ind)
+    rs = np.random.RandomState(0)
+    q0 = torch.from_numpy((mu.numpy()[ind][None] + sigma.numpy()[ind][None] * rs.randn(1024, 40)).astype(np.float32))
+    return spec, q0
+
+
+def test_cfg2_full_size_determinism_and_sharding():
+    """configs[1]: 1024 chains, L = 196, eps = 5e-4 (full trajectory length), 6 iterations: bit-identical when repeated and
+    when the 1024 chains are sharded 4 x 256 with chain_offset (what 4 GPUs would run)."""
+    spec, q0 = _cfg2()
+    kw = dict(num_samples=6, num_steps=196, step_size=5e-4, burn=1, seed=7)
+    a = engine.run_sampler([spec], q0, **kw)
+    b = engine.run_sampler([spec], q0, **kw)
+    assert torch.equal(a.samples, b.samples) and torch.equal(a.hamiltonians, b.hamiltonians)
+    parts = [engine.run_sampler([spec], q0[i * 256:(i + 1) * 256], chain_offset=i * 256, **kw) for i in range(4)]
+    assert torch.equal(torch.cat([p.samples for p in parts], dim=1), a.samples)
+    assert torch.equal(torch.cat([p.accepted for p in parts], dim=1), a.accepted)
+    assert torch.isfinite(a.samples).all() and 0.5 < a.acceptance_rate <= 1.0
+    # energy errors of a 196-step trajectory stay small relative to |H| ~ 1e5 (symplectic integrator, fp32)
+    dH = (a.hamiltonians[..., 0] - a.hamiltonians[..., 1]).abs()
+    assert float(dH.median()) < 50.0
+
+
+@pytest.fixture(scope="module")
+def cfg3():
+    arch = DeepONetArch()
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=1000, n_t=101, n_x=101, seed=0)
+    return arch, x1, x2, y, theta
+
+
+def test_cfg3_full_size_split_closures_sum_to_full(cfg3):
+    """configs[2] at N = 1000, P = 10201, D = 172401: sum of the M = 2 split log-posteriors/gradients (prior_scale 2)
+    equals the full closure (main_HMC_splitting.py:209-258); repeated evaluation is bit-identical."""
+    arch, x1, x2, y, theta = cfg3
+    kw = dict(arch=arch, x2=x2, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
+    full = LogProbSpec(x=x1, y=y, **kw)
+    q = (theta[None] + 0.002 * torch.from_numpy(np.random.RandomState(1).randn(2, arch.num_params).astype(np.float32)))
+    prep = engine.prepare(full)
+    lp, g = engine.logp_grad(prep, q)
+    lp2, g2 = engine.logp_grad(prep, q)
+    assert torch.equal(lp, lp2) and torch.equal(g, g2)
+    parts = [engine.logp_grad(LogProbSpec(x=x1[i * 500:(i + 1) * 500], y=y[i * 500:(i + 1) * 500], prior_scale=2.0, **kw), q)
+             for i in range(2)]
+    lps = (parts[0][0].double() + parts[1][0].double()).cpu().numpy()
+    np.testing.assert_allclose(lps, lp.double().cpu().numpy(), rtol=2e-6)
+    gs = (parts[0][1] + parts[1][1]).cpu().numpy()
+    gf = g.cpu().numpy()
+    np.testing.assert_allclose(gs, gf, rtol=2e-5, atol=2e-5 * np.abs(gf).max())
+
+
+def test_cfg4_full_size_vi_gradient_is_gather_of_full_gradient(cfg3):
+    """configs[3]: the VI-HMC closure over d = 17240 sampled weights equals the full closure evaluated at
+    W = mu with W[ind] = q, gathered at ind (autograd through index_put), up to the prior terms."""
+    arch, x1, x2, y, theta = cfg3
+    mu, sigma, ind = synth.deeponet_vi_artifacts(theta, 0.10, seed=1)
+    kw = dict(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0)
+    # infinite prior sigma removes the prior so only the likelihood is compared
+    inf_d = torch.full((len(ind),), float("inf"))
+    inf_D = torch.full((arch.num_params,), float("inf"))
+    vi = LogProbSpec(frozen=mu, sens_ind=ind, prior_sigma=inf_d, **kw)
+    full = LogProbSpec(prior_sigma=inf_D, **kw)
+    q = mu[ind][None] + 0.003 * torch.from_numpy(np.random.RandomState(2).randn(2, len(ind)).astype(np.float32))
+    W = mu[None].repeat(2, 1)
+    W[:, ind] = q
+    lp_vi, g_vi = engine.logp_grad(vi, q)
+    lp_f, g_f = engine.logp_grad(full, W)
+    assert torch.equal(lp_vi, lp_f)
+    assert torch.equal(g_vi, g_f[:, torch.from_numpy(ind).to(g_f.device)])
+
+
+def test_prior_scale_is_linear(cfg3):
+    """logp(prior_scale = s) = loglik + prior / s: three evaluations determine and check the decomposition."""
+    arch, x1, x2, y, theta = cfg3
+    kw = dict(arch=arch, x=x1[:64], x2=x2[:512], y=y[:64, :512], loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
+    q = theta[None].clone()
+    vals = {s: float(engine.logp_grad(LogProbSpec(prior_scale=s, **kw), q, need_grad=False)[0][0]) for s in (1.0, 2.0, 4.0)}
+    prior = 2.0 * (vals[1.0] - vals[2.0])
+    loglik = vals[1.0] - prior
+    assert abs((loglik + prior / 4.0) - vals[4.0]) <= 2e-6 * abs(vals[4.0]) + 1e-2
