@@ -239,17 +239,19 @@ __global__ void mlp_loss_kernel(const float* __restrict__ O, const float* __rest
   }
 }
 
-// grad[c,i] = dWf[c, ind[i]] - (q - mu) / sigma^2 / prior_scale ; logp[c] = loglik[c] + (sum_i -0.5 (q-mu)^2/sigma^2 + log_norm)/scale
-// one CTA per chain; fixed-order block reduction of the prior.
+// grad[c,i] = dWf[c, ind[i]] - (q - mu) / sigma^2 / prior_scale, plus this slab's share of the prior
+// sum_i -0.5 (q-mu)^2 / sigma^2.  grid (slabs, chains): every CTA streams kFinSlab coordinates of one chain and
+// writes one partial; logp_kernel then adds the partials in fixed order (no float atomics).
+constexpr int kFinSlab = 8192;
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ dWf, const long long* __restrict__ ind,
                                                         const float* __restrict__ q, const float* __restrict__ prior_mu,
                                                         const float* __restrict__ prior_sigma, float sigma_scalar,
-                                                        float inv_scale, float log_norm, const float* __restrict__ loglik,
-                                                        long long D, long long d, float* __restrict__ logp,
+                                                        float inv_scale, long long D, long long d, float* __restrict__ prior_part,
                                                         float* __restrict__ grad) {
-  const long long c = blockIdx.x;
+  const long long c = blockIdx.y;
+  const long long lo = (long long)blockIdx.x * kFinSlab, hi = lo + kFinSlab < d ? lo + kFinSlab : d;
   float lp = 0.0f;
-  for (long long i = threadIdx.x; i < d; i += blockDim.x) {
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float sg = prior_sigma ? __ldg(prior_sigma + i) : sigma_scalar;
     const float iv = isinf(sg) ? 0.0f : 1.0f / (sg * sg);
     const float dq = q[c * d + i] - (prior_mu ? __ldg(prior_mu + i) : 0.0f);
@@ -266,8 +268,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
   if (threadIdx.x == 0) {
     float s = 0.0f;
     for (int w = 0; w < 8; ++w) s += red[w];
-    logp[c] = loglik[c] + (s + log_norm) * inv_scale;
+    prior_part[c * gridDim.x + blockIdx.x] = s;
   }
+}
+
+// logp[c] = loglik[c] + (sum_slabs prior_part[c, :] + log_norm) / prior_scale
+__global__ void logp_kernel(const float* __restrict__ prior_part, int slabs, const float* __restrict__ loglik, float inv_scale,
+                            float log_norm, long long C, float* __restrict__ logp) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.0f;
+  for (int i = 0; i < slabs; ++i) s += prior_part[c * slabs + i];
+  logp[c] = loglik[c] + (s + log_norm) * inv_scale;
 }
 
 // =============================================================================================
@@ -349,7 +361,7 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long f = splitk_scratch_floats(pl.b.dims[l], pl.b.in_of(l), (int)pl.P, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
-  pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.D + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P;
+  pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.D + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
   pl.shared_floats = pl.deeponet ? pl.P * 5 + 64 : 64;
   return VIHMC_OK;
 }
@@ -498,6 +510,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     float* part_ll = bb.take((long long)Cb * tiles);
     float* part_g = bb.take((long long)Cb * tiles);
     float* loglik = bb.take(Cb);
+    float* prior_part = bb.take((long long)Cb * ((d + kFinSlab - 1) / kFinSlab));
     float* scratch = pl.scratch_per_chain > 0 ? bb.take((long long)Cb * pl.scratch_per_chain) : nullptr;
     const float* qb = q + c0 * d;
 
@@ -552,10 +565,13 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
       if (grad != nullptr)
         if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
     }
-    finalize_kernel<<<Cb, 256, 0, st>>>(dWf, reinterpret_cast<const long long*>(p->sens_ind), qb, p->prior_mu, p->prior_sigma,
-                                        p->prior_sigma_scalar, 1.0f / p->prior_scale, p->prior_log_norm, loglik, D, d,
-                                        logp + c0, grad ? grad + c0 * d : nullptr);
+    const int slabs = (int)((d + kFinSlab - 1) / kFinSlab);
+    finalize_kernel<<<dim3(slabs, Cb), 256, 0, st>>>(dWf, reinterpret_cast<const long long*>(p->sens_ind), qb, p->prior_mu,
+                                                     p->prior_sigma, p->prior_sigma_scalar, 1.0f / p->prior_scale, D, d, prior_part,
+                                                     grad ? grad + c0 * d : nullptr);
     VIHMC_LAUNCH_OK("finalize_kernel");
+    logp_kernel<<<(Cb + 127) / 128, 128, 0, st>>>(prior_part, slabs, loglik, 1.0f / p->prior_scale, p->prior_log_norm, Cb, logp + c0);
+    VIHMC_LAUNCH_OK("logp_kernel");
   }
   return VIHMC_OK;
 }
