@@ -213,6 +213,31 @@ VIHMC_API int vihmc_gather_vi(const int64_t* sens_ind, const float* grad_W, floa
                     void* stream);
 
 /*
+ * The dense path's batched-GEMM building block, exported so that every operand staging mode of the tensor-core
+ * kernel can be parity-tested on its own (it replaces the torch.nn.functional.linear / einsum calls of
+ * Operator_network/VI_HMC/my_make_func.py:53-79 and the matmuls autograd derives from them):
+ *   C[b][m, n] = sum_k opA[b][m, k] * opB[b][k, n],   b < batch
+ * with opA[b][m,k] at A + b*a_bs + m*a_sm + k*a_sk, opB[b][k,n] at B + b*b_bs + k*b_sk + n*b_sn and C[b][m,n] at
+ * C + b*c_bs + m*ldc + n (element strides, a batch stride of 0 shares the operand).  use_tensor_cores = 1 runs the
+ * tcgen05 3xTF32 kernel (needs M >= 32, K >= 16), 0 the FP32 SIMT kernel.  K > 2048 with a non-NULL
+ * splitk_scratch (ceil(K/1024) * batch * M * N floats) is split into 1024-deep slices summed in fixed order.
+ */
+VIHMC_API int vihmc_gemm_batched(const float* A, int64_t a_bs, int64_t a_sm, int64_t a_sk, const float* B, int64_t b_bs,
+                       int64_t b_sk, int64_t b_sn, float* C, int64_t c_bs, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                       int32_t batch, int32_t use_tensor_cores, float* splitk_scratch, void* stream);
+
+/*
+ * Test hook: ONE tcgen05.mma kind::tf32 (M = N = 128, K = 8, FP32 accumulate from zero) whose A / B shared-memory
+ * tiles are copied verbatim from two 8 KB device images, with the given descriptor byte strides (leading / stride
+ * byte offset), descriptor layout types (0 = no swizzle, 1 = 128B base 32B, 2 = 128B, 4 = 64B, 6 = 32B) and extra
+ * instruction-descriptor bits (1<<15: A is MN-major, 1<<16: B is MN-major).  out = D[128,128].
+ * Used by the tests to pin the operand layouts the staging code writes against what the tensor core reads.
+ */
+VIHMC_API int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo,
+                     uint32_t b_sbo, uint32_t a_layout_type, uint32_t b_layout_type, uint32_t idesc_extra, float* out,
+                     void* stream);
+
+/*
  * Host-buffer convenience entry (everything is a HOST pointer, including those inside prob): allocates
  * device memory, copies in, runs vihmc_mlp_sample or vihmc_sample, copies samples/diagnostics out.
  */

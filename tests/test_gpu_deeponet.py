@@ -1,6 +1,8 @@
 """GPU parity tests for the dense path (DeepONet and wide MLP) and the large-d building blocks, through the C ABI.
 
 Tolerance: log-posterior and gradient within rtol 1e-5 (fp32), gradient taken relative to its largest component."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -238,3 +240,38 @@ def test_data_sharded_sampler_equals_general_sampler():
     np.testing.assert_allclose((parts[0][0] + parts[1][0]).cpu().numpy(), lp_full.cpu().numpy(), rtol=2e-6)
     gs = (parts[0][1] + parts[1][1]).cpu().numpy()
     np.testing.assert_allclose(gs, g_full.cpu().numpy(), rtol=2e-5, atol=2e-5 * np.abs(gs).max())
+
+
+def _gemm_case(rs, batch, M, N, K, a_layout, b_layout, dev):
+    """a_layout / b_layout: 'k' = reduction dimension contiguous, 'mn' = M (resp. N) contiguous, 'odd' = K-contiguous
+    with a row stride that is not a multiple of 4 floats (scalar staging), 'shared' = one matrix for the whole batch."""
+    def make(rows, cols, layout):   # logical [batch, rows, cols(K)] for A; B is built as [batch, N, K] and transposed
+        if layout == "k":
+            return torch.from_numpy(rs.randn(batch, rows, cols).astype(np.float32)).to(dev)
+        if layout == "mn":
+            return torch.from_numpy(rs.randn(batch, cols, rows).astype(np.float32)).to(dev).transpose(1, 2)
+        if layout == "odd":
+            return torch.from_numpy(rs.randn(batch, rows, cols + 1).astype(np.float32)).to(dev)[:, :, :cols]
+        if layout == "shared":
+            return torch.from_numpy(rs.randn(1, rows, cols).astype(np.float32)).to(dev).expand(batch, -1, -1)
+        raise ValueError(layout)
+    A = make(M, K, a_layout)
+    B = make(N, K, b_layout).transpose(1, 2)
+    return A, B
+
+
+@pytest.mark.parametrize("a_layout,b_layout", [("k", "k"), ("k", "mn"), ("mn", "mn"), ("mn", "k"), ("odd", "k"), ("k", "odd"),
+                                               ("shared", "mn"), ("mn", "shared")])
+@pytest.mark.parametrize("shape", [(3, 35, 16, 16), (2, 300, 100, 100), (2, 100, 100, 1030), (1, 130, 37, 2500), (2, 64, 8, 600)])
+def test_tensor_core_gemm_every_staging_mode_vs_fp64(a_layout, b_layout, shape):
+    """vihmc_gemm_batched on the tcgen05 3xTF32 kernel against an fp64 matmul, for K-major, MN-major and scalar operand
+    staging, ragged tiles (M, N, K off the 128 / 16 grid, M or N not a multiple of 4) and split-K (K > 2048)."""
+    batch, M, N, K = shape
+    dev = torch.device("cuda:0")
+    A, B = _gemm_case(np.random.RandomState(zlib.crc32(repr((a_layout, b_layout, shape)).encode())), batch, M, N, K, a_layout, b_layout, dev)
+    ref = torch.matmul(A.double(), B.double())
+    for tc in (True, False):
+        got = engine.gemm_batched(A, B, tensor_cores=tc)
+        err = (got.double() - ref).abs().max().item()
+        scale = (A.double().abs() @ B.double().abs()).max().item()   # sum_k |a||b|: the natural error scale of a dot product
+        assert err <= 2e-6 * scale, (tc, err, scale)

@@ -24,6 +24,11 @@ size_t dense_workspace_bytes(const vihmc_problem*, long long C);
 int dense_logp_grad(const vihmc_problem*, long long C, const float* q, float* logp, float* grad, void* ws, size_t ws_bytes,
                     cudaStream_t);
 int dense_predict(const vihmc_problem*, long long C, const float* q, float* out, void* ws, size_t ws_bytes, cudaStream_t);
+int dense_umma_probe(const float* a_img, const float* b_img, unsigned a_lbo, unsigned a_sbo, unsigned b_lbo, unsigned b_sbo,
+                     unsigned a_type, unsigned b_type, unsigned idesc_extra, float* out, cudaStream_t);
+int dense_gemm(const float* A, long long a_bs, long long a_sm, long long a_sk, const float* B, long long b_bs, long long b_sk,
+               long long b_sn, float* C, long long c_bs, long long ldc, int M, int N, int K, int batch, int use_tc, float* scratch,
+               cudaStream_t);
 int row_partials(long long d);
 int launch_momentum(unsigned long long, long long, long long, long long, long long, float*, cudaStream_t);
 int launch_uniform(unsigned long long, long long, long long, long long, float*, cudaStream_t);
@@ -496,6 +501,21 @@ int vihmc_sample_host(const vihmc_problem* probs_host, int32_t n_problems, const
     if (io_host->step_sizes) VIHMC_CUDA_OK(cudaMemcpy(io_host->step_sizes, io.step_sizes, C * sizeof(float), cudaMemcpyDeviceToHost));
   }
   return VIHMC_OK;
+}
+
+int vihmc_gemm_batched(const float* A, int64_t a_bs, int64_t a_sm, int64_t a_sk, const float* B, int64_t b_bs, int64_t b_sk,
+                       int64_t b_sn, float* C, int64_t c_bs, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t batch,
+                       int32_t use_tensor_cores, float* splitk_scratch, void* stream) {
+  if (int rc = device_check()) return rc;
+  return dense_gemm(A, a_bs, a_sm, a_sk, B, b_bs, b_sk, b_sn, C, c_bs, ldc, M, N, K, batch, use_tensor_cores, splitk_scratch,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                     uint32_t a_layout_type, uint32_t b_layout_type, uint32_t idesc_extra, float* out, void* stream) {
+  if (int rc = device_check()) return rc;
+  return dense_umma_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, a_layout_type, b_layout_type, idesc_extra, out,
+                          static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -13,19 +13,19 @@
 // partials + a second pass), never float atomics, so accept/reject is reproducible.
 //
 // Data layout in HBM for one batch of Cb chains (all fp32, row-major):
-//   Wf  [Cb, D]            full weights (VI scatter of q into the frozen means)
+//   Wf  [Cb, Dp]           full weights (VI scatter of q into the frozen means) in a PADDED layout: every tensor starts
+//                          on a 16-byte boundary and weight rows are padded to a multiple of 4 floats, so every GEMM
+//                          operand can be staged with float4 loads (flat index -> padded position: pad_map[D])
 //   act_a[l] [Cb, N, w]    branch activations after layer l;  act_b[l] [Cb, P, w] trunk activations
-//   G   [Cb, N, P]         d loglik / d output (the only [N,P]-sized per-chain buffer)
+//   G   [Cb, N, Pp]        d loglik / d output (the only [N,P]-sized per-chain buffer; rows padded to Pp = 4*ceil(P/4))
 //   dz0/dz1 [Cb, R, w]     ping-pong pre-activation gradients, R = max(N, P)
-//   dWf [Cb, D]            gradient w.r.t. the full weight vector; gathered to grad[C, d] at the end
+//   dWf [Cb, Dp]           gradient w.r.t. the full weight vector (padded layout); gathered to grad[C, d] at the end
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
 namespace vihmc {
-
-int launch_scatter(const float*, const long long*, const float*, float*, long long, long long, long long, cudaStream_t);
 
 // =============================================================================================
 // batched SGEMM  C[b] = opA(A[b]) (MxK) * opB(B[b]) (KxN), generic element strides, fused epilogues
@@ -161,10 +161,11 @@ static bool tensor_cores_enabled() {
 }
 
 template <int EPI>
-static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scratch = nullptr) {
+static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scratch = nullptr, int force = -1) {
   if (g.M < 1 || g.N < 1 || g.K < 1 || batch < 1) return fail(VIHMC_ERR_INVALID, "gemm: empty problem");
   if (batch > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch > 65535");
-  if (tensor_cores_enabled() && tc_gemm_eligible(g)) return launch_tc_gemm<EPI>(g, batch, st, scratch);
+  const bool tc = force < 0 ? tensor_cores_enabled() && tc_gemm_eligible(g) : force == 1;
+  if (tc) return launch_tc_gemm<EPI>(g, batch, st, scratch);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
   sgemm_batched_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
   VIHMC_LAUNCH_OK("sgemm_batched_kernel");
@@ -246,8 +247,8 @@ constexpr int kFinSlab = 8192;
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ dWf, const long long* __restrict__ ind,
                                                         const float* __restrict__ q, const float* __restrict__ prior_mu,
                                                         const float* __restrict__ prior_sigma, float sigma_scalar,
-                                                        float inv_scale, long long D, long long d, float* __restrict__ prior_part,
-                                                        float* __restrict__ grad) {
+                                                        float inv_scale, long long Dp, long long d, const int* __restrict__ pad_map,
+                                                        float* __restrict__ prior_part, float* __restrict__ grad) {
   const long long c = blockIdx.y;
   const long long lo = (long long)blockIdx.x * kFinSlab, hi = lo + kFinSlab < d ? lo + kFinSlab : d;
   float lp = 0.0f;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     lp = fmaf(-0.5f * dq * dq, iv, lp);
     if (grad != nullptr) {
       const long long f = ind ? __ldg(ind + i) : i;
-      grad[c * d + i] = fmaf(-dq * iv, inv_scale, dWf[c * D + f]);
+      grad[c * d + i] = fmaf(-dq * iv, inv_scale, dWf[c * Dp + __ldg(pad_map + f)]);
     }
   }
   __shared__ float red[8];
@@ -282,13 +283,49 @@ __global__ void logp_kernel(const float* __restrict__ prior_part, int slabs, con
   logp[c] = loglik[c] + (s + log_norm) * inv_scale;
 }
 
+// ---- padded weight layout ----
+// one tensor of the flat parameter vector: flat [flat0, flat0+numel) viewed as rows of `in` floats -> pad0 + row*ld + col
+struct PadSeg { long long flat0, numel, pad0; int in, ld; };
+struct PadTable { int n; PadSeg seg[4 * VIHMC_MAX_LAYERS + 1]; };
+
+__global__ void pad_map_kernel(PadTable t, long long D, int* __restrict__ pad_map) {
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= D) return;
+  for (int s = 0; s < t.n; ++s) {
+    const PadSeg& g = t.seg[s];
+    if (f < g.flat0 + g.numel) {
+      const long long r = f - g.flat0;
+      pad_map[f] = (int)(g.pad0 + (r / g.in) * g.ld + (r % g.in));
+      return;
+    }
+  }
+}
+
+// Wf[c, pad_map[f]] = src[f]  (src = frozen means shared by every chain, or -- full HMC -- the chain's own q row)
+__global__ void __launch_bounds__(256) scatter_fill_padded_kernel(const float* __restrict__ src, long long src_cs,
+                                                                  const int* __restrict__ pad_map, float* __restrict__ Wf,
+                                                                  long long D, long long Dp) {
+  const long long c = blockIdx.y;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < D; f += (long long)gridDim.x * blockDim.x)
+    Wf[c * Dp + __ldg(pad_map + f)] = src[c * src_cs + f];
+}
+// Wf[c, pad_map[ind[i]]] = q[c, i]   (my_make_func.py:56-57; ind sorted ascending => near-coalesced)
+__global__ void __launch_bounds__(256) scatter_put_padded_kernel(const long long* __restrict__ ind, const float* __restrict__ q,
+                                                                 const int* __restrict__ pad_map, float* __restrict__ Wf,
+                                                                 long long d, long long Dp) {
+  const long long c = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (long long)gridDim.x * blockDim.x)
+    Wf[c * Dp + __ldg(pad_map + __ldg(ind + i))] = q[c * d + i];
+}
+
 // =============================================================================================
 // host orchestration
 // =============================================================================================
 struct Stack {
   int n_layers, in_dim;
   int dims[VIHMC_MAX_LAYERS];
-  long long w_off[VIHMC_MAX_LAYERS], b_off[VIHMC_MAX_LAYERS];
+  long long w_off[VIHMC_MAX_LAYERS], b_off[VIHMC_MAX_LAYERS];   // offsets in the PADDED layout
+  int ldw[VIHMC_MAX_LAYERS];                                     // padded weight row stride
   bool has_bias[VIHMC_MAX_LAYERS];
   int in_of(int l) const { return l == 0 ? in_dim : dims[l - 1]; }
   int max_width() const {
@@ -298,24 +335,36 @@ struct Stack {
   }
 };
 
-static long long build_stack(Stack& s, int n_layers, int in_dim, const int32_t* dims, long long off, bool last_bias) {
+static inline long long pad4(long long v) { return (v + 3) / 4 * 4; }
+
+// lays one stack out after flat offset `off` / padded offset `poff`; appends its tensors to the pad table
+static void build_stack(Stack& s, int n_layers, int in_dim, const int32_t* dims, long long& off, long long& poff, bool last_bias,
+                        PadTable& tbl) {
   s.n_layers = n_layers;
   s.in_dim = in_dim;
   for (int l = 0; l < n_layers; ++l) {
     s.dims[l] = dims[l];
-    s.w_off[l] = off;
-    off += (long long)dims[l] * s.in_of(l);
+    const int in = s.in_of(l);
+    s.ldw[l] = (int)pad4(in);
+    s.w_off[l] = poff;
+    tbl.seg[tbl.n++] = PadSeg{off, (long long)dims[l] * in, poff, in, s.ldw[l]};
+    off += (long long)dims[l] * in;
+    poff += (long long)dims[l] * s.ldw[l];
     s.has_bias[l] = (l < n_layers - 1) || last_bias;
-    s.b_off[l] = off;
-    if (s.has_bias[l]) off += dims[l];
+    s.b_off[l] = poff;
+    if (s.has_bias[l]) {
+      tbl.seg[tbl.n++] = PadSeg{off, dims[l], poff, dims[l], dims[l]};
+      off += dims[l];
+      poff += pad4(dims[l]);
+    }
   }
-  return off;
 }
 
 struct DensePlan {
   bool deeponet;
   Stack a, b;       // MLP: a only
-  long long D, N, P, R;
+  long long D, Dp, N, P, Pp, R;   // Dp, Pp: padded parameter count / padded trunk-point row length
+  PadTable tbl;
   int K;            // DeepONet: output_neurons
   long long head_tiles, loss_tiles;
   // per-chain float counts
@@ -327,21 +376,30 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
   pl.deeponet = p->model_kind == VIHMC_MODEL_DEEPONET;
   pl.N = p->N;
   pl.P = pl.deeponet ? p->P : 1;
-  long long off;
+  if (p->n_layers_a < 1 || p->n_layers_a > VIHMC_MAX_LAYERS || p->n_layers_b < 0 || p->n_layers_b > VIHMC_MAX_LAYERS)
+    return fail(VIHMC_ERR_INVALID, "layer counts out of range");
+  pl.Pp = pad4(pl.P);
+  pl.tbl.n = 0;
+  long long off = 0, poff = 0;
   if (pl.deeponet) {
-    off = build_stack(pl.a, p->n_layers_a, p->in_a, p->dims_a, 1, true);
-    off = build_stack(pl.b, p->n_layers_b, p->in_b, p->dims_b, off, true);
+    pl.tbl.seg[pl.tbl.n++] = PadSeg{0, 1, 0, 1, 1};   // scalar output bias b0 = W[0] (my_make_func.py:52)
+    off = 1;
+    poff = 4;
+    build_stack(pl.a, p->n_layers_a, p->in_a, p->dims_a, off, poff, true, pl.tbl);
+    build_stack(pl.b, p->n_layers_b, p->in_b, p->dims_b, off, poff, true, pl.tbl);
     pl.K = p->dims_a[p->n_layers_a - 1];
     if (p->dims_b[p->n_layers_b - 1] != pl.K) return fail(VIHMC_ERR_INVALID, "branch and trunk output widths differ");
     if (p->impose_bc && p->in_b != 5) return fail(VIHMC_ERR_INVALID, "impose_bc needs in_trunk = 5");
   } else {
-    off = build_stack(pl.a, p->n_layers_a, p->in_a, p->dims_a, 0, p->last_bias != 0);
+    build_stack(pl.a, p->n_layers_a, p->in_a, p->dims_a, off, poff, p->last_bias != 0, pl.tbl);
     pl.b.n_layers = 0;
     pl.K = 1;
     if (p->dims_a[p->n_layers_a - 1] != 1) return fail(VIHMC_ERR_UNSUPPORTED, "dense MLP path needs out_dim = 1");
   }
   if (off != p->D) return fail(VIHMC_ERR_INVALID, "D=%lld does not match the architecture (%lld)", (long long)p->D, off);
+  if (poff > 0x7fffffffLL) return fail(VIHMC_ERR_UNSUPPORTED, "more than 2^31 parameters per chain");
   pl.D = p->D;
+  pl.Dp = poff;
   pl.R = pl.N > pl.P ? pl.N : pl.P;
   pl.act_a_floats = 0;
   for (int l = 0; l < pl.a.n_layers; ++l) pl.act_a_floats += pl.N * pl.a.dims[l];
@@ -351,7 +409,7 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
   pl.head_tiles = ((pl.P + BN - 1) / BN) * ((pl.N + BM - 1) / BM);
   pl.loss_tiles = (pl.N + 255) / 256;
   const long long tiles = pl.deeponet ? pl.head_tiles : pl.loss_tiles;
-  const long long G = pl.deeponet ? pl.N * pl.P : pl.N;
+  const long long G = pl.deeponet ? pl.N * pl.Pp : pl.N;
   pl.scratch_per_chain = 0;   // split-K partials of the largest weight-gradient GEMM
   for (int l = 0; l < pl.a.n_layers; ++l) {
     const long long f = splitk_scratch_floats(pl.a.dims[l], pl.a.in_of(l), (int)pl.N, 1);
@@ -361,8 +419,9 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long f = splitk_scratch_floats(pl.b.dims[l], pl.b.in_of(l), (int)pl.P, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
-  pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.D + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
-  pl.shared_floats = pl.deeponet ? pl.P * 5 + 64 : 64;
+  pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
+  // shared by every chain: pad map, trunk features, padded copy of the targets
+  pl.shared_floats = pl.D + 64 + (pl.deeponet ? pl.P * 5 + 64 + pl.N * pl.Pp + 64 : 0);
   return VIHMC_OK;
 }
 
@@ -406,7 +465,7 @@ struct Bump {
 };
 }  // namespace
 
-// forward of one stack for Cb chains: in [R, in_dim] shared -> acts[l] [Cb, R, dims[l]]
+// forward of one stack for Cb chains: in [R, in_dim] shared -> acts[l] [Cb, R, dims[l]]   (D = padded per-chain stride of Wf)
 static int stack_forward(const Stack& s, const float* input, long long R, const float* Wf, long long D, float* const* acts,
                          int act, bool act_on_last, int Cb, cudaStream_t st) {
   for (int l = 0; l < s.n_layers; ++l) {
@@ -414,7 +473,7 @@ static int stack_forward(const Stack& s, const float* input, long long R, const 
     const int in = s.in_of(l), out = s.dims[l];
     g.A = l == 0 ? input : acts[l - 1];
     g.a_bs = l == 0 ? 0 : R * in; g.a_sm = in; g.a_sk = 1;
-    g.B = Wf + s.w_off[l]; g.b_bs = D; g.b_sk = 1; g.b_sn = in;   // opB[k,n] = W[n,k]
+    g.B = Wf + s.w_off[l]; g.b_bs = D; g.b_sk = 1; g.b_sn = s.ldw[l];   // opB[k,n] = W[n,k]
     g.C = acts[l]; g.c_bs = R * out; g.ldc = out;
     g.M = (int)R; g.N = out; g.K = in;
     const bool last = l == s.n_layers - 1;
@@ -438,7 +497,7 @@ static int stack_backward(const Stack& s, const float* input, long long R, const
     GemmArgs g{};
     g.A = dz_cur; g.a_bs = R * out; g.a_sm = 1; g.a_sk = out;            // opA[m=o,k=r] = dz[r,o]
     g.B = l == 0 ? input : acts[l - 1]; g.b_bs = l == 0 ? 0 : R * in; g.b_sk = in; g.b_sn = 1;
-    g.C = dWf + s.w_off[l]; g.c_bs = D; g.ldc = in;
+    g.C = dWf + s.w_off[l]; g.c_bs = D; g.ldc = s.ldw[l];
     g.M = out; g.N = in; g.K = (int)R;
     if (int rc = launch_gemm<EPI_STORE>(g, Cb, st, scratch)) return rc;
     if (s.has_bias[l]) {
@@ -449,7 +508,7 @@ static int stack_backward(const Stack& s, const float* input, long long R, const
       // dz_prev[r,i] = (sum_o dz[r,o] W[o,i]) * act'(a_{l-1}[r,i])
       GemmArgs h{};
       h.A = dz_cur; h.a_bs = R * out; h.a_sm = out; h.a_sk = 1;
-      h.B = Wf + s.w_off[l]; h.b_bs = D; h.b_sk = in; h.b_sn = 1;       // opB[k=o,n=i] = W[o,i]
+      h.B = Wf + s.w_off[l]; h.b_bs = D; h.b_sk = s.ldw[l]; h.b_sn = 1;   // opB[k=o,n=i] = W[o,i]
       h.C = dz_other; h.c_bs = R * in; h.ldc = in;
       h.M = (int)R; h.N = in; h.K = out;
       h.aux = acts[l - 1]; h.aux_bs = R * in; h.ld_aux = in; h.act = act;
@@ -457,6 +516,63 @@ static int stack_backward(const Stack& s, const float* input, long long R, const
       float* t = dz_cur; dz_cur = dz_other; dz_other = t;
     }
   }
+  return VIHMC_OK;
+}
+
+// chain-independent buffers at the head of the workspace: pad map, trunk features, padded targets
+struct SharedBufs {
+  const int* pad_map;
+  const float* trunk_in;
+  const float* y_pad;   // [N, Pp] (DeepONet) or p->y
+  float* batch_base;
+};
+
+static int prepare_shared(const vihmc_problem* p, const DensePlan& pl, void* ws, bool need_targets, cudaStream_t st, SharedBufs& sb) {
+  Bump bump(static_cast<float*>(ws));
+  int* map = reinterpret_cast<int*>(bump.take(pl.D));
+  pad_map_kernel<<<(unsigned)((pl.D + 255) / 256), 256, 0, st>>>(pl.tbl, pl.D, map);
+  VIHMC_LAUNCH_OK("pad_map_kernel");
+  sb.pad_map = map;
+  sb.trunk_in = nullptr;
+  sb.y_pad = p->y;
+  if (pl.deeponet) {
+    if (p->impose_bc) {
+      float* feats = bump.take(pl.P * 5);
+      trunk_features_kernel<<<(unsigned)((pl.P + 255) / 256), 256, 0, st>>>(p->x2, pl.P, feats);
+      VIHMC_LAUNCH_OK("trunk_features_kernel");
+      sb.trunk_in = feats;
+    } else {
+      sb.trunk_in = p->x2;
+    }
+    if (need_targets) {
+      if (pl.Pp != pl.P) {   // rows of the targets on 16-byte boundaries: the head epilogue reads them with float4 loads
+        float* yp = bump.take(pl.N * pl.Pp);
+        VIHMC_CUDA_OK(cudaMemsetAsync(yp, 0, sizeof(float) * pl.N * pl.Pp, st));
+        VIHMC_CUDA_OK(cudaMemcpy2DAsync(yp, sizeof(float) * pl.Pp, p->y, sizeof(float) * pl.P, sizeof(float) * pl.P, (size_t)pl.N,
+                                        cudaMemcpyDeviceToDevice, st));
+        sb.y_pad = yp;
+      }
+    }
+  }
+  sb.batch_base = bump.take(0);
+  return VIHMC_OK;
+}
+
+// Wf[c] = padded(frozen with q scattered at sens_ind)   (my_make_func.py:48-50 / :56-57)
+static int scatter_padded(const vihmc_problem* p, const DensePlan& pl, const int* pad_map, const float* qb, float* Wf, int Cb,
+                          cudaStream_t st) {
+  const long long D = pl.D, d = p->d;
+  const unsigned gx = (unsigned)((D + 1023) / 1024 < 148 * 4 ? (D + 1023) / 1024 : 148 * 4);
+  if (p->frozen == nullptr) {
+    scatter_fill_padded_kernel<<<dim3(gx, Cb), 256, 0, st>>>(qb, D, pad_map, Wf, D, pl.Dp);
+    VIHMC_LAUNCH_OK("scatter_fill_padded_kernel");
+    return VIHMC_OK;
+  }
+  scatter_fill_padded_kernel<<<dim3(gx, Cb), 256, 0, st>>>(p->frozen, 0, pad_map, Wf, D, pl.Dp);
+  VIHMC_LAUNCH_OK("scatter_fill_padded_kernel");
+  const unsigned gd = (unsigned)((d + 1023) / 1024 < 148 * 4 ? (d + 1023) / 1024 : 148 * 4);
+  scatter_put_padded_kernel<<<dim3(gd, Cb), 256, 0, st>>>(reinterpret_cast<const long long*>(p->sens_ind), qb, pad_map, Wf, d, pl.Dp);
+  VIHMC_LAUNCH_OK("scatter_put_padded_kernel");
   return VIHMC_OK;
 }
 
@@ -475,36 +591,25 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
   const long long cb_max = chains_per_batch(pl, C, ws_bytes - shared_bytes);
   if (cb_max < 1) return fail(VIHMC_ERR_WORKSPACE, "workspace too small for one chain: need %lld bytes", pl.per_chain_floats * 4 + (long long)shared_bytes);
   const Likelihood lik = make_likelihood(p->loss, p->tau_out);
-  const long long D = pl.D, d = p->d, N = pl.N, P = pl.P;
+  const long long Dp = pl.Dp, d = p->d, N = pl.N, P = pl.P, Pp = pl.Pp;
   const int wmax = pl.a.max_width() > pl.b.max_width() ? pl.a.max_width() : pl.b.max_width();
 
-  Bump bump(static_cast<float*>(ws));
-  float* feats = nullptr;
-  const float* trunk_in = nullptr;
-  if (pl.deeponet) {
-    if (p->impose_bc) {
-      feats = bump.take(P * 5);
-      trunk_features_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(p->x2, P, feats);
-      VIHMC_LAUNCH_OK("trunk_features_kernel");
-      trunk_in = feats;
-    } else {
-      trunk_in = p->x2;
-    }
-  }
-  float* batch_base = bump.take(0);
+  SharedBufs sb;
+  if (int rc = prepare_shared(p, pl, ws, predict_out == nullptr, st, sb)) return rc;
+  const float* trunk_in = sb.trunk_in;
 
   for (long long c0 = 0; c0 < C; c0 += cb_max) {
     const int Cb = (int)((C - c0) < cb_max ? (C - c0) : cb_max);
-    Bump bb(batch_base);
-    float* Wf = bb.take((long long)Cb * D);
-    float* dWf = bb.take((long long)Cb * D);
+    Bump bb(sb.batch_base);
+    float* Wf = bb.take((long long)Cb * Dp);
+    float* dWf = bb.take((long long)Cb * Dp);
     float* acts_a[VIHMC_MAX_LAYERS];
     float* acts_b[VIHMC_MAX_LAYERS];
     for (int l = 0; l < pl.a.n_layers; ++l) acts_a[l] = bb.take((long long)Cb * N * pl.a.dims[l]);
     for (int l = 0; l < pl.b.n_layers; ++l) acts_b[l] = bb.take((long long)Cb * P * pl.b.dims[l]);
     const long long tiles = pl.deeponet ? pl.head_tiles : pl.loss_tiles;
     float* G = nullptr;
-    if (predict_out == nullptr || !pl.deeponet) G = bb.take((long long)Cb * (pl.deeponet ? N * P : N));
+    if (predict_out == nullptr || !pl.deeponet) G = bb.take((long long)Cb * (pl.deeponet ? N * Pp : N));
     float* dz0 = bb.take((long long)Cb * pl.R * wmax);
     float* dz1 = bb.take((long long)Cb * pl.R * wmax);
     float* part_ll = bb.take((long long)Cb * tiles);
@@ -514,10 +619,10 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     float* scratch = pl.scratch_per_chain > 0 ? bb.take((long long)Cb * pl.scratch_per_chain) : nullptr;
     const float* qb = q + c0 * d;
 
-    if (int rc = launch_scatter(p->frozen, reinterpret_cast<const long long*>(p->sens_ind), qb, Wf, Cb, D, d, st)) return rc;
-    if (int rc = stack_forward(pl.a, p->x, N, Wf, D, acts_a, p->act, false, Cb, st)) return rc;
+    if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st)) return rc;
+    if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
     if (pl.deeponet)
-      if (int rc = stack_forward(pl.b, trunk_in, P, Wf, D, acts_b, p->act, false, Cb, st)) return rc;
+      if (int rc = stack_forward(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
 
     if (pl.deeponet) {
       // head: O = Bout * Tout^T + b0 ; fused residual / loglik partials
@@ -529,29 +634,29 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
       g.B = Tout; g.b_bs = P * K; g.b_sk = 1; g.b_sn = K;
       g.M = (int)N; g.N = (int)P; g.K = K;
       if (predict_out != nullptr) return fail(VIHMC_ERR_INVALID, "internal: DeepONet predict goes through dense_predict");
-      g.C = G; g.c_bs = N * P; g.ldc = P;
-      g.bias = Wf; g.bias_bs = D;                    // scalar output bias is W[0] (my_make_func.py:52)
-      g.aux = p->y; g.aux_bs = 0; g.ld_aux = P;
+      g.C = G; g.c_bs = N * Pp; g.ldc = Pp; g.row_pad_ok = 1;   // G and the padded targets have Pp floats per row
+      g.bias = Wf; g.bias_bs = Dp;                   // scalar output bias is W[0] (my_make_func.py:52)
+      g.aux = sb.y_pad; g.aux_bs = 0; g.ld_aux = Pp;
       g.ll_const = lik.ll_const; g.half_prec = lik.half_prec; g.prec = lik.prec;
       g.part_ll = part_ll; g.part_g = part_g;
       if (int rc = launch_gemm<EPI_HEAD>(g, Cb, st)) return rc;
       reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, tiles, Cb, loglik, 1);
       if (grad != nullptr) {
-        reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_g, tiles, Cb, dWf, D);  // d/d b0 = sum G
+        reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_g, tiles, Cb, dWf, Dp);  // d/d b0 = sum G
         // dBout[n,k] = sum_p G[n,p] Tout[p,k]
         GemmArgs h{};
-        h.A = G; h.a_bs = N * P; h.a_sm = P; h.a_sk = 1;
+        h.A = G; h.a_bs = N * Pp; h.a_sm = Pp; h.a_sk = 1;
         h.B = Tout; h.b_bs = P * K; h.b_sk = K; h.b_sn = 1;
         h.C = dz0; h.c_bs = N * K; h.ldc = K; h.M = (int)N; h.N = K; h.K = (int)P;
         if (int rc = launch_gemm<EPI_STORE>(h, Cb, st)) return rc;
-        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
         // dTout[p,k] = sum_n G[n,p] Bout[n,k]
         GemmArgs t{};
-        t.A = G; t.a_bs = N * P; t.a_sm = 1; t.a_sk = P;
+        t.A = G; t.a_bs = N * Pp; t.a_sm = 1; t.a_sk = Pp;
         t.B = Bout; t.b_bs = N * K; t.b_sk = K; t.b_sn = 1;
         t.C = dz0; t.c_bs = P * K; t.ldc = K; t.M = (int)P; t.N = K; t.K = (int)N;
         if (int rc = launch_gemm<EPI_STORE>(t, Cb, st)) return rc;
-        if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, D, acts_b, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dz0, dz1, p->act, Cb, st, scratch)) return rc;
       }
     } else {
       const float* O = acts_a[pl.a.n_layers - 1];
@@ -563,16 +668,39 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
       VIHMC_LAUNCH_OK("mlp_loss_kernel");
       reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, tiles, Cb, loglik, 1);
       if (grad != nullptr)
-        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, D, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
     }
     const int slabs = (int)((d + kFinSlab - 1) / kFinSlab);
     finalize_kernel<<<dim3(slabs, Cb), 256, 0, st>>>(dWf, reinterpret_cast<const long long*>(p->sens_ind), qb, p->prior_mu,
-                                                     p->prior_sigma, p->prior_sigma_scalar, 1.0f / p->prior_scale, D, d, prior_part,
-                                                     grad ? grad + c0 * d : nullptr);
+                                                     p->prior_sigma, p->prior_sigma_scalar, 1.0f / p->prior_scale, Dp, d, sb.pad_map,
+                                                     prior_part, grad ? grad + c0 * d : nullptr);
     VIHMC_LAUNCH_OK("finalize_kernel");
     logp_kernel<<<(Cb + 127) / 128, 128, 0, st>>>(prior_part, slabs, loglik, 1.0f / p->prior_scale, p->prior_log_norm, Cb, logp + c0);
     VIHMC_LAUNCH_OK("logp_kernel");
   }
+  return VIHMC_OK;
+}
+
+// vihmc_gemm_batched (include/vihmc.h)
+int dense_gemm(const float* A, long long a_bs, long long a_sm, long long a_sk, const float* B, long long b_bs, long long b_sk,
+               long long b_sn, float* C, long long c_bs, long long ldc, int M, int N, int K, int batch, int use_tc, float* scratch,
+               cudaStream_t st) {
+  if (A == nullptr || B == nullptr || C == nullptr) return fail(VIHMC_ERR_INVALID, "gemm: null operand");
+  if (use_tc && (M < 32 || K < 16)) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: the tensor-core kernel needs M >= 32 and K >= 16");
+  GemmArgs g{};
+  g.A = A; g.a_bs = a_bs; g.a_sm = a_sm; g.a_sk = a_sk;
+  g.B = B; g.b_bs = b_bs; g.b_sk = b_sk; g.b_sn = b_sn;
+  g.C = C; g.c_bs = c_bs; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  return launch_gemm<EPI_STORE>(g, batch, st, scratch, use_tc ? 1 : 0);
+}
+
+// vihmc_debug_umma (include/vihmc.h): layout probe of one tcgen05.mma
+int dense_umma_probe(const float* a_img, const float* b_img, unsigned a_lbo, unsigned a_sbo, unsigned b_lbo, unsigned b_sbo,
+                     unsigned a_type, unsigned b_type, unsigned idesc_extra, float* out, cudaStream_t st) {
+  if (a_img == nullptr || b_img == nullptr || out == nullptr) return fail(VIHMC_ERR_INVALID, "umma probe: null pointer");
+  VIHMC_CUDA_OK(cudaFuncSetAttribute(tc::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kProbeSmem));
+  tc::umma_probe_kernel<<<1, 128, tc::kProbeSmem, st>>>(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, a_type, b_type, tc::kIdesc | idesc_extra, out);
+  VIHMC_LAUNCH_OK("umma_probe_kernel");
   return VIHMC_OK;
 }
 
@@ -592,29 +720,22 @@ int dense_predict(const vihmc_problem* p, long long C, const float* q, float* ou
   if (ws_bytes <= shared_bytes) return fail(VIHMC_ERR_WORKSPACE, "workspace too small");
   const long long cb_max = chains_per_batch(pl, C, ws_bytes - shared_bytes);
   if (cb_max < 1) return fail(VIHMC_ERR_WORKSPACE, "workspace too small for one chain");
-  const long long D = pl.D, d = p->d, N = pl.N, P = pl.P;
-  Bump bump(static_cast<float*>(ws));
-  const float* trunk_in = p->x2;
-  if (p->impose_bc) {
-    float* feats = bump.take(P * 5);
-    trunk_features_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(p->x2, P, feats);
-    VIHMC_LAUNCH_OK("trunk_features_kernel");
-    trunk_in = feats;
-  }
-  float* batch_base = bump.take(0);
+  const long long Dp = pl.Dp, d = p->d, N = pl.N, P = pl.P;
+  SharedBufs sb;
+  if (int rc = prepare_shared(p, pl, ws, false, st, sb)) return rc;
   for (long long c0 = 0; c0 < C; c0 += cb_max) {
     const int Cb = (int)((C - c0) < cb_max ? (C - c0) : cb_max);
-    Bump bb(batch_base);
-    float* Wf = bb.take((long long)Cb * D);
-    bb.take((long long)Cb * D);
+    Bump bb(sb.batch_base);
+    float* Wf = bb.take((long long)Cb * Dp);
+    bb.take((long long)Cb * Dp);
     float* acts_a[VIHMC_MAX_LAYERS];
     float* acts_b[VIHMC_MAX_LAYERS];
     for (int l = 0; l < pl.a.n_layers; ++l) acts_a[l] = bb.take((long long)Cb * N * pl.a.dims[l]);
     for (int l = 0; l < pl.b.n_layers; ++l) acts_b[l] = bb.take((long long)Cb * P * pl.b.dims[l]);
     float* part = bb.take(2LL * Cb * pl.head_tiles);
-    if (int rc = launch_scatter(p->frozen, reinterpret_cast<const long long*>(p->sens_ind), q + c0 * d, Wf, Cb, D, d, st)) return rc;
-    if (int rc = stack_forward(pl.a, p->x, N, Wf, D, acts_a, p->act, false, Cb, st)) return rc;
-    if (int rc = stack_forward(pl.b, trunk_in, P, Wf, D, acts_b, p->act, false, Cb, st)) return rc;
+    if (int rc = scatter_padded(p, pl, sb.pad_map, q + c0 * d, Wf, Cb, st)) return rc;
+    if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
+    if (int rc = stack_forward(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
     // O = Bout Tout^T + b0 through the HEAD epilogue with a zero target and prec = -1: C = -(-1) * (O - 0) = O
     GemmArgs g{};
     const int K = pl.K;
@@ -622,11 +743,11 @@ int dense_predict(const vihmc_problem* p, long long C, const float* q, float* ou
     g.B = acts_b[pl.b.n_layers - 1]; g.b_bs = P * K; g.b_sk = 1; g.b_sn = K;
     g.M = (int)N; g.N = (int)P; g.K = K;
     g.C = out + c0 * N * P; g.c_bs = N * P; g.ldc = P;
-    g.bias = Wf; g.bias_bs = D;
+    g.bias = Wf; g.bias_bs = Dp;
     g.part_ll = part; g.part_g = part + (long long)Cb * pl.head_tiles;
     g.prec = -1.0f;
-    float* zero_row = bb.take(P);   // target row of zeros shared by every output row (ld_aux = 0)
-    VIHMC_CUDA_OK(cudaMemsetAsync(zero_row, 0, sizeof(float) * P, st));
+    float* zero_row = bb.take(pl.Pp);   // target row of zeros shared by every output row (ld_aux = 0)
+    VIHMC_CUDA_OK(cudaMemsetAsync(zero_row, 0, sizeof(float) * pl.Pp, st));
     g.aux = zero_row; g.aux_bs = 0; g.ld_aux = 0;
     if (int rc = launch_gemm<EPI_HEAD>(g, Cb, st)) return rc;
   }

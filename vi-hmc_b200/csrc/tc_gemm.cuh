@@ -12,10 +12,13 @@
 // 2 CTAs / SM, so no third CTA sits spinning in tcgen05.alloc so one CTA's
 // epilogue overlaps another's main loop):
 //   * all 8 warps stream the A / B k-tiles (16 floats deep) from global memory through registers, split
-//     them, and store hi/lo tiles in the UMMA canonical K-major no-swizzle layout (8x16B core matrices);
-//     arbitrary element strides are supported, so transposed operands (dW = dZ^T X, dX = dZ W) and
-//     rows that are not 16-byte aligned (101-wide branch input) need no extra copies -- this is also
-//     why the operands are not staged with TMA: the split needs the values in registers anyway.
+//     them, and store hi/lo tiles as 8x16B core matrices (no swizzle).  Three staging modes per operand:
+//       KVEC   K is the contiguous dimension (activations, W[n,k]): float4 loads along K, K-major tile;
+//       MNVEC  M/N is the contiguous dimension (dZ^T, X in dW = dZ^T X; W in dX = dZ W; G^T): float4 loads
+//              along M/N stored as an MN-major tile -- the tensor core transposes (instruction-descriptor
+//              a_major / b_major bits), so no operand is ever transposed through registers or copied;
+//       SCALAR any element strides / alignment (101-wide branch input): predicated scalar loads, K-major.
+//     The split needs the values in registers anyway, which is why the operands are not staged with TMA.
 //   * three smem stages; thread 0 issues 3 MMAs per 8-deep k-step and commits to the stage's mbarrier;
 //     the next tile's global loads are in flight while the tensor core works.
 //   * epilogue: 8 warps read the accumulators with tcgen05.ld (warp w -> TMEM lanes 32*(w%4).., column
@@ -44,6 +47,7 @@ struct GemmArgs {
   const float* bias; long long bias_bs;   // [N] per batch (EPI_BIAS_ACT) or scalar per batch (EPI_HEAD)
   const float* aux; long long aux_bs, ld_aux;  // activation (EPI_DACT) or Y (EPI_HEAD; aux_bs = 0: shared)
   int act;
+  int row_pad_ok;   // rows of C and aux are allocated up to round_up(N, 4) floats: float4 access may straddle N
   float ll_const, half_prec, prec;
   float* part_ll; float* part_g;          // [batch, tiles] (EPI_HEAD)
   // split-K (EPI_STORE only): blockIdx.z = b * splits + s handles k in [s*kc, min(K,(s+1)*kc)) and writes its
@@ -66,18 +70,29 @@ constexpr int SMEM_BYTES = (EPI_BYTES > STAGES * STAGE_BYTES ? EPI_BYTES : STAGE
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell; bits 61-63 = layout type).
+// K-major tile, no swizzle (type 0): core matrix = 8 rows x 16 B of K; LBO = bytes between the K chunks, SBO = bytes
+//   between 8-row groups.
+// MN-major tile: for 32-bit operands the tensor core only transposes the SWIZZLE_128B_BASE32B layout (type 1) -- every
+//   other layout type returns zeros for an MN-major tf32 operand (measured with vihmc_debug_umma,
+//   tools/probe_umma_layout.py, which also pinned the word map below).  An atom is 4 k-rows x 32 M/N elements (512 B):
+//     byte(k, n) = (n/32)*LBO + (k/4)*SBO + (k%4)*128 + ((((n%32)/8) ^ (k%4))*32) + (n%8)*4
+//   i.e. each k-row is 128 B of 32 consecutive M/N elements whose four 32-byte chunks are XOR-ed with the row index.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)layout_type << 61);
 }
+constexpr int MN_LBO = 512;                    // MN-major tile: the four 32-element M/N atoms of a k-atom are contiguous
+constexpr int MN_SBO = (BM / 32) * MN_LBO;     // 2 KB: one 4-deep K atom of 128 rows
+constexpr uint32_t MN_LAYOUT = 1;              // SWIZZLE_128B_BASE32B
 
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = BN (cute::UMMA::InstrDescriptor bit layout)
+// kind::tf32, FP32 accumulate, M = 128, N = BN (cute::UMMA::InstrDescriptor bit layout); bit 15 / 16 = A / B is MN-major
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc),
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
       "r"(accumulate)
       : "memory");
 }
@@ -107,11 +122,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Truncating instead (v & 0xFFFFE000) shrinks every operand toward zero, i.e. a coherent ~1e-6 relative
 // bias on every output; sums with heavy cancellation (d/d b0 = sum of G over N*P outputs) then miss the
 // 1e-5 parity bar.  With rounding the per-product error is zero-mean.
-__device__ __forceinline__ float rna_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
+// rna = round to nearest, ties away from zero, on the sign-magnitude bit pattern: add half a tf32 ulp and clear
+// the 13 low mantissa bits.  Two integer instructions; `cvt.rna.tf32.f32` compiles to the same pair plus an
+// Inf/NaN guard (FSETP + predicate), which finite network values do not need (a non-finite value stays non-finite
+// or becomes NaN, and the sampler rejects either).
+__device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   hi.x = rna_tf32(v.x); lo.x = rna_tf32(v.x - hi.x);
   hi.y = rna_tf32(v.y); lo.y = rna_tf32(v.y - hi.y);
@@ -119,28 +134,53 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   hi.w = rna_tf32(v.w); lo.w = rna_tf32(v.w - hi.w);
 }
 
+enum LoadMode { LOAD_SCALAR = 0, LOAD_KVEC = 1, LOAD_MNVEC = 2 };
+
 // One operand tile: rows [r0, r0+128) x k [k0, k0+16).  Element (r, k) lives at base + r*s_r + k*s_k.
-// A warp instruction covers one 8-row group x 4 chunks: lane -> (row r8 = lane%8, chunk = lane/8), which
-// makes the 16-byte shared-memory stores conflict-free and reads 64 contiguous bytes per row.
+//   K-major modes: a warp instruction covers one 8-row group x 4 chunks: lane -> (row r8 = lane%8, chunk = lane/8),
+//     which makes the 16-byte shared-memory stores conflict-free and reads 64 contiguous bytes per row.
+//   MNVEC: a thread's float4 is 4 consecutive rows at one k; (warp, i) -> atom, lane -> (k row, 4-row block), see fetch().
 struct TileLoader {
   const float* base;
   long long s_r, s_k;
   int R, K, r0;
-  bool vec;   // K-contiguous and 16-byte aligned: float4 loads
+  int mode;
   __device__ __forceinline__ void fetch(int k0, int tid, float4 (&v)[2]) const {
     const int lane = tid & 31, warp = tid >> 5;
+    if (mode == LOAD_MNVEC) {
+      // (warp, i) -> one atom: 4 k-rows x 32 rows; lane -> (k row lane%4, 4-row block lane/4): a k-row is 128 contiguous bytes
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int atom = warp * 2 + i;   // mn atom = atom % 4, k atom = atom / 4
+        const int k = k0 + (atom >> 2) * 4 + (lane & 3);
+        const int r = r0 + (atom & 3) * 32 + (lane >> 2) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K && r < R) {
+          const float* p = base + r + (long long)k * s_k;
+          if (r + 3 < R) {
+            x = __ldg(reinterpret_cast<const float4*>(p));
+          } else {
+            x.x = __ldg(p);
+            if (r + 1 < R) x.y = __ldg(p + 1);
+            if (r + 2 < R) x.z = __ldg(p + 2);
+          }
+        }
+        v[i] = x;
+      }
+      return;
+    }
     const int r8 = lane & 7, ch = lane >> 3;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = r0 + (i * 8 + warp) * 8 + r8;
       const int k = k0 + ch * 4;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < R) {
+      if (r < R && k < K) {
         const float* p = base + (long long)r * s_r + (long long)k * s_k;
-        if (vec) {
-          if (k < K) x = __ldg(reinterpret_cast<const float4*>(p));   // K % 4 == 0 on this path
+        if (mode == LOAD_KVEC && k + 3 < K) {
+          x = __ldg(reinterpret_cast<const float4*>(p));
         } else {
-          if (k + 0 < K) x.x = __ldg(p);
+          x.x = __ldg(p);
           if (k + 1 < K) x.y = __ldg(p + s_k);
           if (k + 2 < K) x.z = __ldg(p + 2 * s_k);
           if (k + 3 < K) x.w = __ldg(p + 3 * s_k);
@@ -151,17 +191,29 @@ struct TileLoader {
   }
 };
 
-__device__ __forceinline__ void stash(unsigned char* hi_tile, unsigned char* lo_tile, int tid, const float4 (&v)[2]) {
+__device__ __forceinline__ void stash(unsigned char* hi_tile, unsigned char* lo_tile, int tid, int mode, const float4 (&v)[2]) {
   const int lane = tid & 31, warp = tid >> 5;
-  const int r8 = lane & 7, ch = lane >> 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const int off = (i * 8 + warp) * SBO + ch * LBO + r8 * 16;
+    int off;
+    if (mode == LOAD_MNVEC) {
+      // a quarter warp (4 k-rows x 2 half chunks) covers 8 distinct 16-byte bank groups: conflict-free
+      const int atom = warp * 2 + i, k4 = lane & 3;
+      off = (atom & 3) * MN_LBO + (atom >> 2) * MN_SBO + k4 * 128 + (((lane >> 3) ^ k4) * 32) + ((lane >> 2) & 1) * 16;
+    } else {
+      off = (i * 8 + warp) * SBO + (lane >> 3) * LBO + (lane & 7) * 16;
+    }
     float4 hi, lo;
     split4(v[i], hi, lo);
     *reinterpret_cast<float4*>(hi_tile + off) = hi;
     *reinterpret_cast<float4*>(lo_tile + off) = lo;
   }
+}
+
+// operand descriptor of the ks-th K = 8 step inside a staged 16-deep tile
+__device__ __forceinline__ uint64_t step_desc(uint32_t tile_saddr, int mode, int ks) {
+  return mode == LOAD_MNVEC ? make_desc(tile_saddr + (uint32_t)ks * 2u * MN_SBO, MN_LBO, MN_SBO, MN_LAYOUT)
+                            : make_desc(tile_saddr + (uint32_t)ks * 2u * LBO, LBO, SBO);
 }
 
 
@@ -189,7 +241,7 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, const float* til
   };
   if (vec) {
     const int c = lane * 4;
-    if (n0 + c < g.N) {   // N % 4 == 0: the whole float4 is in range
+    if (n0 + c < g.N) {
       const float4 v = *reinterpret_cast<const float4*>(tile_row + c);
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
       if (EPI == EPI_BIAS_ACT) {
@@ -199,8 +251,13 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, const float* til
         if (vec_aux) av = __ldg(reinterpret_cast<const float4*>(arow + c));
         else { av.x = __ldg(arow + c); av.y = __ldg(arow + c + 1); av.z = __ldg(arow + c + 2); av.w = __ldg(arow + c + 3); }
       }
+      // N % 4 != 0 only with row_pad_ok: the float4 is in memory, the columns past N get zeros and no likelihood terms
+      const int nv = g.N - (n0 + c);
       float4 o;
-      o.x = apply(v.x, bv.x, av.x); o.y = apply(v.y, bv.y, av.y); o.z = apply(v.z, bv.z, av.z); o.w = apply(v.w, bv.w, av.w);
+      o.x = apply(v.x, bv.x, av.x);
+      o.y = nv > 1 ? apply(v.y, bv.y, av.y) : 0.0f;
+      o.z = nv > 2 ? apply(v.z, bv.z, av.z) : 0.0f;
+      o.w = nv > 3 ? apply(v.w, bv.w, av.w) : 0.0f;
       *reinterpret_cast<float4*>(crow + c) = o;
     }
   } else {
@@ -215,13 +272,13 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, const float* til
   }
 }
 
-__device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, long long ld, int N) {
-  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && bs % 4 == 0 && ld % 4 == 0 && N % 4 == 0;
+__device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, long long ld, int N, int row_pad_ok) {
+  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && bs % 4 == 0 && ld % 4 == 0 && (N % 4 == 0 || row_pad_ok);
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_vec, int b_vec) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];   // swizzled MN-major tiles need 1 KB-aligned bases
   unsigned char* smem = smem_raw;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SMEM_BYTES - 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BYTES - 64);
@@ -253,8 +310,9 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
 
-  TileLoader la{g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_vec != 0};
-  TileLoader lb{g.B + (long long)b * g.b_bs, g.b_sn, g.b_sk, g.N, g.K, n0, b_vec != 0};
+  TileLoader la{g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_mode};
+  TileLoader lb{g.B + (long long)b * g.b_bs, g.b_sn, g.b_sk, g.N, g.K, n0, b_mode};
+  const uint32_t idesc = kIdesc | (a_mode == LOAD_MNVEC ? 1u << 15 : 0u) | (b_mode == LOAD_MNVEC ? 1u << 16 : 0u);
 
   const int nk = (g.K + BK - 1) / BK;
   float4 ra[2], rb[2];
@@ -264,8 +322,8 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
     const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
     if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
-    stash(st, st + TILE_BYTES, tid, ra);
-    stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, rb);
+    stash(st, st + TILE_BYTES, tid, a_mode, ra);
+    stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, b_mode, rb);
     if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
       la.fetch((kt + 1) * BK, tid, ra);
       lb.fetch((kt + 1) * BK, tid, rb);
@@ -278,17 +336,16 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
       const int k_left = g.K - kt * BK;
       const int steps = k_left > 8 ? 2 : 1;
       for (int ks = 0; ks < steps; ++ks) {
-        const uint32_t koff = (uint32_t)ks * 2u * LBO;   // one K=8 step = two 16-byte chunks
-        const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa + TILE_BYTES + koff);
-        const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES + koff), b_lo = make_desc(sa + 3 * TILE_BYTES + koff);
+        const uint64_t a_hi = step_desc(sa, a_mode, ks), a_lo = step_desc(sa + TILE_BYTES, a_mode, ks);
+        const uint64_t b_hi = step_desc(sa + 2 * TILE_BYTES, b_mode, ks), b_lo = step_desc(sa + 3 * TILE_BYTES, b_mode, ks);
         // The tensor core's fp32 accumulate rounds toward zero: every accumulate step shrinks the running sum
         // by up to one ulp, a COHERENT bias that grows with the number of chained MMAs.  The two correction
         // products therefore get their own accumulator (columns BN..2BN): the main chain sees one accumulate
         // per k-step instead of three, and the correction chain's truncation is 2^-11 smaller.
         const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
-        mma_tf32(tmem_d, a_hi, b_hi, acc);
-        mma_tf32(tmem_d + BN, a_lo, b_hi, acc);
-        mma_tf32(tmem_d + BN, a_hi, b_lo, 1u);
+        mma_tf32(tmem_d, a_hi, b_hi, idesc, acc);
+        mma_tf32(tmem_d + BN, a_lo, b_hi, idesc, acc);
+        mma_tf32(tmem_d + BN, a_hi, b_lo, idesc, 1u);
       }
       mma_commit(&mbar[s]);
     }
@@ -327,8 +384,8 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
   const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)b * g.bias_bs) : 0.0f;
   const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs : nullptr;
   const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
-  const bool vec = rows_vec_ok(g.C, g.c_bs, g.ldc, g.N);
-  const bool vec_aux = auxb != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N);
+  const bool vec = rows_vec_ok(g.C, g.c_bs, g.ldc, g.N, g.row_pad_ok);
+  const bool vec_aux = auxb != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N, g.row_pad_ok);
   float ll_acc = 0.0f, g_acc = 0.0f;
 #pragma unroll 2
   for (int r = warp; r < BM; r += THREADS / 32) {
@@ -360,232 +417,61 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_v
 
 }  // namespace tc
 
-// =============================================================================================
-// Persistent, warp-specialised variant (opt-in, VIHMC_TC_PERSISTENT=1): one CTA per SM loops over output tiles.
-//   warps 0-7   producers: global -> registers -> 3xTF32 split -> shared-memory stage (4-stage ring, full/empty
-//               mbarriers), running ahead of the tensor core by up to four k-tiles, across tile boundaries;
-//   warp  8     MMA issuer: waits full[s], issues the three tcgen05.mma of each k-step into accumulator set
-//               a = tile & 1 (TMEM columns a*256 .. a*256+255: main + correction), tcgen05.commit -> empty[s];
-//               after the last k-tile tcgen05.commit -> tmem_full[a];
-//   warps 9-16  epilogue (two per TMEM lane quarter, 64 columns each): wait tmem_full[a], tcgen05.ld the 128x128 accumulators into a shared staging tile,
-//               release the accumulator set (tmem_empty[a]) so the MMAs of tile i+2 can start, then the
-//               row-wise coalesced epilogue of tile i runs while the tensor core works on tile i+1.
-// Compared with the one-tile-per-CTA kernel this removes the per-tile TMEM allocation / barrier setup and
-// overlaps epilogue and main loop inside one SM (K = 100 layers have only 7 k-tiles per tile).
-// =============================================================================================
-namespace tcws {
-
-using namespace tc;
-constexpr int WS_STAGES = 4;
-constexpr int PRODUCER_WARPS = 8, EPI_WARPS = 8;
-constexpr int WS_THREADS = (PRODUCER_WARPS + 1 + EPI_WARPS) * 32;   // 544
-constexpr int WS_EPI_OFF = WS_STAGES * STAGE_BYTES;                  // 128 KB of operand stages
-constexpr int WS_BAR_OFF = WS_EPI_OFF + EPI_BYTES;                   // + 67,584 B staging tile
-constexpr int WS_SMEM_BYTES = WS_BAR_OFF + 256;
-constexpr int EPI_BAR_ID = 1;                                        // named barrier of the 128 epilogue threads
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR_ID), "n"(EPI_WARPS * 32) : "memory"); }
-
-struct TileCoord {
-  int b, m0, n0, K;
-  const float *A, *B;
-  float* C;
-  long long c_bs, ldc;
-  long long tile_linear;   // index into the per-batch partial arrays (EPI_HEAD)
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, long long t, int tiles_n, int tiles_m) {
-  TileCoord tc;
-  const int bx = (int)(t % tiles_n), by = (int)((t / tiles_n) % tiles_m), bz = (int)(t / ((long long)tiles_n * tiles_m));
-  const bool split = g.splits > 1;
-  tc.b = split ? bz / g.splits : bz;
-  const int ks = split ? bz % g.splits : 0;
-  tc.m0 = by * BM;
-  tc.n0 = bx * BN;
-  tc.A = g.A + (long long)tc.b * g.a_bs;
-  tc.B = g.B + (long long)tc.b * g.b_bs;
-  tc.K = g.K;
-  tc.C = g.C + (long long)tc.b * g.c_bs;
-  tc.c_bs = g.c_bs;
-  tc.ldc = g.ldc;
-  if (split) {
-    const int k_lo = ks * g.kc;
-    tc.A += (long long)k_lo * g.a_sk;
-    tc.B += (long long)k_lo * g.b_sk;
-    tc.K = (g.K - k_lo) < g.kc ? (g.K - k_lo) : g.kc;
-    tc.C = g.split_buf + ((long long)ks * g.batch + tc.b) * (long long)g.M * g.N;
-    tc.ldc = g.N;
-  }
-  tc.tile_linear = (long long)by * tiles_n + bx;
-  return tc;
-}
-
-template <int EPI>
-__global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(GemmArgs g, int a_vec, int b_vec, int tiles_n, int tiles_m,
-                                                                   long long total_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* smem = smem_raw;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WS_BAR_OFF);          // [WS_STAGES]
-  uint64_t* empty = full + WS_STAGES;                                       // [WS_STAGES]
-  uint64_t* tmem_full = empty + WS_STAGES;                                  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;                                     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* red = reinterpret_cast<float*>(tmem_slot + 4);                     // [2 * EPI_WARPS]
+// ---------------------------------------------------------------------------------------------
+// Layout probe (test hook, vihmc_debug_umma): ONE tcgen05.mma kind::tf32 (M = 128, N = 128, K = 8) on operand tiles
+// taken verbatim from two 8 KB images, with caller-chosen descriptor strides and instruction descriptor.  Feeding an
+// identity-like A and B[i] = i makes D spell out which shared-memory word the tensor core reads for every (k, n):
+// this is how the MN-major staging layout above was pinned on hardware (tests/test_gpu_deeponet.py).
+// ---------------------------------------------------------------------------------------------
+namespace tc {
+constexpr int kProbeSmem = 96 * 1024;
+__global__ void __launch_bounds__(128) umma_probe_kernel(const float* __restrict__ a_img, const float* __restrict__ b_img,
+                                                         uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                                                         uint32_t a_type, uint32_t b_type, uint32_t idesc, float* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char tiles[];   // A image, B image, then zero-filled guard space
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
+  for (int i = tid; i < kProbeSmem / 4; i += 128) reinterpret_cast<float*>(tiles)[i] = 0.0f;
+  __syncthreads();
+  for (int i = tid; i < TILE_BYTES / 4; i += 128) {
+    reinterpret_cast<float*>(tiles)[i] = a_img[i];
+    reinterpret_cast<float*>(tiles + TILE_BYTES)[i] = b_img[i];
+  }
   if (tid == 0) {
-    for (int s = 0; s < WS_STAGES; ++s) {
-      mbar_init(&full[s], PRODUCER_WARPS);
-      mbar_init(&empty[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 1);
-    }
+    mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == PRODUCER_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < PRODUCER_WARPS) {
-    // ===================== producers =====================
-    uint32_t it = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(g, t, tiles_n, tiles_m);
-      TileLoader la{tc.A, g.a_sm, g.a_sk, g.M, tc.K, tc.m0, a_vec != 0};
-      TileLoader lb{tc.B, g.b_sn, g.b_sk, g.N, tc.K, tc.n0, b_vec != 0};
-      const int nk = (tc.K + BK - 1) / BK;
-      float4 ra[2], rb[2];
-      la.fetch(0, tid, ra);
-      lb.fetch(0, tid, rb);
-      for (int kt = 0; kt < nk; ++kt, ++it) {
-        const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1u;
-        unsigned char* st = smem + s * STAGE_BYTES;
-        mbar_wait(&empty[s], ph ^ 1u);
-        stash(st, st + TILE_BYTES, tid, ra);
-        stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, rb);
-        if (kt + 1 < nk) {
-          la.fetch((kt + 1) * BK, tid, ra);
-          lb.fetch((kt + 1) * BK, tid, rb);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
-      }
-    }
-  } else if (warp == PRODUCER_WARPS) {
-    // ===================== MMA issuer =====================
-    uint32_t it = 0, tcount = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
-      const TileCoord tc = decode_tile(g, t, tiles_n, tiles_m);
-      const int nk = (tc.K + BK - 1) / BK;
-      const uint32_t a = tcount & 1u;
-      mbar_wait(&tmem_empty[a], ((tcount >> 1) & 1u) ^ 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_main = tmem_base + a * 256u, d_corr = d_main + (uint32_t)BN;
-      for (int kt = 0; kt < nk; ++kt, ++it) {
-        const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const int steps = (tc.K - kt * BK) > 8 ? 2 : 1;
-          for (int ks = 0; ks < steps; ++ks) {
-            const uint32_t koff = (uint32_t)ks * 2u * LBO;
-            const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa + TILE_BYTES + koff);
-            const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES + koff), b_lo = make_desc(sa + 3 * TILE_BYTES + koff);
-            const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
-            mma_tf32(d_main, a_hi, b_hi, acc);
-            mma_tf32(d_corr, a_lo, b_hi, acc);
-            mma_tf32(d_corr, a_hi, b_lo, 1u);
-          }
-          mma_commit(&empty[s]);                       // stage reusable once these MMAs have read it
-          if (kt == nk - 1) mma_commit(&tmem_full[a]); // accumulators of this tile complete
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===================== epilogue =====================
-    const int e = warp - PRODUCER_WARPS - 1;          // 0..7
-    const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int half = e >> 2;                          // which 64 accumulator columns this warp drains
-    float* tile = reinterpret_cast<float*>(smem + WS_EPI_OFF);
-    uint32_t tcount = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tcount) {
-      const TileCoord tc = decode_tile(g, t, tiles_n, tiles_m);
-      const uint32_t a = tcount & 1u;
-      mbar_wait(&tmem_full[a], (tcount >> 1) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // phase 1: TMEM -> staging tile (thread = accumulator row q*32+lane, 64 columns)
-      {
-        float* trow = tile + (q * 32 + lane) * TILE_LD + half * (BN / 2);
-        const uint32_t tbase = tmem_base + a * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
-#pragma unroll 2
-        for (int cc = 0; cc < BN / 2; cc += 8) {
-          uint32_t r[8], rc[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                       : "r"(tbase + (uint32_t)cc));
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
-                       : "r"(tbase + (uint32_t)(BN + cc)));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-          *reinterpret_cast<float4*>(trow + cc) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(trow + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      epi_bar();                                       // tile staged, every TMEM read of this set retired
-      if (e == 0 && lane == 0) mbar_arrive(&tmem_empty[a]);
-      // phase 2: row-wise coalesced epilogue
-      const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)tc.b * g.bias_bs) : 0.0f;
-      const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)tc.b * g.aux_bs : nullptr;
-      const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)tc.b * g.bias_bs : nullptr;
-      const bool vec = rows_vec_ok(tc.C, tc.c_bs, tc.ldc, g.N) && (tc.n0 % 4 == 0);
-      const bool vec_aux = auxb != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N);
-      float ll_acc = 0.0f, g_acc = 0.0f;
-#pragma unroll 2
-      for (int r = e; r < BM; r += EPI_WARPS) {
-        const int m = tc.m0 + r;
-        if (m >= g.M) break;
-        epilogue_row<EPI>(g, tile + r * TILE_LD, tc.C + (long long)m * tc.ldc + tc.n0,
-                          auxb ? auxb + (long long)m * g.ld_aux + tc.n0 : nullptr, biasb, tc.n0, lane, vec, vec_aux, bias0, ll_acc,
-                          g_acc);
-      }
-      if (EPI == EPI_HEAD) {
-        ll_acc = warp_sum(ll_acc);
-        g_acc = warp_sum(g_acc);
-        if (lane == 0) { red[e] = ll_acc; red[EPI_WARPS + e] = g_acc; }
-      }
-      epi_bar();                                       // staging tile free for the next tile; partial sums visible
-      if (EPI == EPI_HEAD && e == 0 && lane == 0) {
-        float s0 = 0.0f, s1 = 0.0f;
-        for (int w = 0; w < EPI_WARPS; ++w) { s0 += red[w]; s1 += red[EPI_WARPS + w]; }
-        const long long tiles = (long long)tiles_n * tiles_m;
-        g.part_ll[(long long)tc.b * tiles + tc.tile_linear] = s0;
-        g.part_g[(long long)tc.b * tiles + tc.tile_linear] = s1;
-      }
-    }
+  const uint32_t tmem_d = tmem_slot;
+  if (tid == 0) {
+    mma_tf32(tmem_d, make_desc(smem_u32(tiles), a_lbo, a_sbo, a_type), make_desc(smem_u32(tiles + TILE_BYTES), b_lbo, b_sbo, b_type),
+             idesc, 0u);
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int cc = 0; cc < 128; cc += 8) {
+    uint32_t r[8];
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 8; ++j) out[(warp * 32 + lane) * 128 + cc + j] = __uint_as_float(r[j]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == PRODUCER_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u) : "memory");
 }
-
-}  // namespace tcws
+}  // namespace tc
 
 // C[b, m, n] = sum_s split_buf[s, b, m, n] in fixed order (fp32 round-to-nearest adds)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ buf, int splits, int batch, int M, int N,
@@ -612,11 +498,18 @@ inline long long splitk_scratch_floats(int M, int N, int K, int batch) {
 // shapes the tensor-core kernel is used for; everything else stays on the FP32-SIMT kernel
 inline bool tc_gemm_eligible(const GemmArgs& g) { return g.M >= 32 && g.K >= 16 && (g.N >= 16 || g.K >= 512); }
 
+// staging mode of one operand: element (r, k) at base + b*bs + r*s_r + k*s_k
+inline int operand_mode(const float* base, long long bs, long long s_r, long long s_k) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && bs % 4 == 0;
+  if (aligned && s_k == 1 && s_r % 4 == 0) return tc::LOAD_KVEC;
+  if (aligned && s_r == 1 && s_k % 4 == 0) return tc::LOAD_MNVEC;
+  return tc::LOAD_SCALAR;
+}
+
 template <int EPI>
 static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch = nullptr) {
-  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const int a_vec = g.a_sk == 1 && g.a_sm % 4 == 0 && g.a_bs % 4 == 0 && g.K % 4 == 0 && aligned16(g.A);
-  const int b_vec = g.b_sk == 1 && g.b_sn % 4 == 0 && g.b_bs % 4 == 0 && g.K % 4 == 0 && aligned16(g.B);
+  const int a_mode = operand_mode(g.A, g.a_bs, g.a_sm, g.a_sk);
+  const int b_mode = operand_mode(g.B, g.b_bs, g.b_sn, g.b_sk);
   auto k = tc::tc_gemm_kernel<EPI>;
   static bool configured = false;
   if (!configured) {
@@ -633,36 +526,10 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     g.split_buf = scratch;
     if ((long long)batch * g.splits > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch * splits > 65535");
   }
-  // The persistent warp-specialised kernel (tcws) is opt-in: measured 21.4 ms vs 18.6 ms per 64-chain DeepONet
-  // gradient batch -- with K = 100 the epilogue is as heavy as the main loop, and 8 of 17 warps doing it lose to
-  // 16 warps (2 CTAs) that all take part in every phase.
-  static const bool simple = []() {
-    const char* e = getenv("VIHMC_TC_PERSISTENT");
-    return !(e != nullptr && e[0] == '1');
-  }();
   const int tiles_n = (g.N + tc::BN - 1) / tc::BN, tiles_m = (g.M + tc::BM - 1) / tc::BM;
-  if (simple) {
-    dim3 grid(tiles_n, tiles_m, batch * g.splits);
-    k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_vec, b_vec);
-    VIHMC_LAUNCH_OK("tc_gemm_kernel");
-  } else {
-    auto kw = tcws::tc_gemm_ws_kernel<EPI>;
-    static bool configured_ws = false;
-    if (!configured_ws) {
-      VIHMC_CUDA_OK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, tcws::WS_SMEM_BYTES));
-      configured_ws = true;
-    }
-    const long long total = (long long)tiles_n * tiles_m * batch * g.splits;
-    static const int num_sms = []() {
-      int dev = 0, n = 148;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-      return n;
-    }();
-    const int grid = (int)(total < num_sms ? total : num_sms);   // persistent: one CTA per SM
-    kw<<<grid, tcws::WS_THREADS, tcws::WS_SMEM_BYTES, st>>>(g, a_vec, b_vec, tiles_n, tiles_m, total);
-    VIHMC_LAUNCH_OK("tc_gemm_ws_kernel");
-  }
+  dim3 grid(tiles_n, tiles_m, batch * g.splits);
+  k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+  VIHMC_LAUNCH_OK("tc_gemm_kernel");
   if (g.splits > 1) {
     const long long total = (long long)batch * g.M * g.N;
     long long blocks = (total + 255) / 256;

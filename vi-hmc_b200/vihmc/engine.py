@@ -153,6 +153,25 @@ def predict(spec, q: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gemm_batched(A: torch.Tensor, B: torch.Tensor, tensor_cores: bool = True) -> torch.Tensor:
+    """C[b] = A[b] @ B[b] through vihmc_gemm_batched.  A [batch, M, K] and B [batch, K, N] are CUDA fp32 tensors or
+    strided VIEWS of them (e.g. `.transpose(1, 2)`, `.expand(batch, -1, -1)`): the element strides are passed as
+    they are, which is how the tests reach every operand staging mode of the tensor-core kernel."""
+    assert A.is_cuda and B.is_cuda and A.dtype == torch.float32 and B.dtype == torch.float32
+    batch, M, K = A.shape
+    _, _, N = B.shape
+    dev = A.device
+    out = torch.empty(batch, M, N, dtype=torch.float32, device=dev)
+    scratch = None
+    if tensor_cores and K > 2048:
+        scratch = torch.empty(((K + 1023) // 1024) * batch * M * N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vihmc_gemm_batched(A.data_ptr(), A.stride(0), A.stride(1), A.stride(2), B.data_ptr(), B.stride(0),
+                                                  B.stride(1), B.stride(2), out.data_ptr(), M * N, N, M, N, K, batch,
+                                                  1 if tensor_cores else 0, _ptr(scratch), _stream(dev)))
+    return out
+
+
 @dataclass
 class SampleResult:
     samples: torch.Tensor                  # [num_samples - burn, C, d]; row 0 is params_init
