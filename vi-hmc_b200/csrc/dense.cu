@@ -189,22 +189,48 @@ __global__ void trunk_features_kernel(const float* __restrict__ x2, long long P,
   F[5 * p + 4] = cosf(four_pi * x);
 }
 
-// out[b, n] = sum_r Z[b, r, n]   (bias gradients).  grid (ceil(n/32), batch), block (32, 8)
-__global__ void colsum_kernel(const float* __restrict__ Z, long long z_bs, long long R, int ncols, long long ldz,
-                              float* __restrict__ out, long long out_bs) {
+// out[b, n] = sum_r Z[b, r, n]   (bias gradients), two fixed-order passes so that the [R, n] slab of every chain is
+// streamed by R/128 CTAs instead of one: pass 1, grid (slabs, batch), block (32, 8): part[b, slab, n] = sum of the
+// slab's 128 rows; pass 2 (colsum_finish_kernel): out[b, n] = sum_slab part[b, slab, n].
+constexpr int kColsumRows = 128;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, long long z_bs, long long R, int ncols, long long ldz,
+                                                     float* __restrict__ part) {
   __shared__ float red[8][33];
-  const int b = blockIdx.y;
-  const int col = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.0f;
-  if (col < ncols)
-    for (long long r = threadIdx.y; r < R; r += 8) s += Z[(long long)b * z_bs + r * ldz + col];
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && col < ncols) {
-    float t = 0.0f;
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[(long long)b * out_bs + col] = t;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const long long r_lo = (long long)slab * kColsumRows, r_hi = r_lo + kColsumRows < R ? r_lo + kColsumRows : R;
+  const float* Zb = Z + (long long)b * z_bs;
+  for (int col0 = 0; col0 < ncols; col0 += 32) {
+    const int col = col0 + threadIdx.x;
+    float s = 0.0f;
+    if (col < ncols)
+      for (long long r = r_lo + threadIdx.y; r < r_hi; r += 8) s += Zb[r * ldz + col];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < ncols) {
+      float t = 0.0f;
+      for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+      part[((long long)b * gridDim.x + slab) * ncols + col] = t;
+    }
+    __syncthreads();
   }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int slabs, int ncols, float* __restrict__ out, long long out_bs) {
+  const int b = blockIdx.x;
+  for (int col = threadIdx.x; col < ncols; col += blockDim.x) {
+    float s = 0.0f;
+    for (int i = 0; i < slabs; ++i) s += part[((long long)b * slabs + i) * ncols + col];
+    out[(long long)b * out_bs + col] = s;
+  }
+}
+// `part` needs batch * ceil(R/128) * ncols floats
+static int launch_colsum(const float* Z, long long z_bs, long long R, int ncols, long long ldz, float* part, float* out,
+                         long long out_bs, int batch, cudaStream_t st) {
+  const int slabs = (int)((R + kColsumRows - 1) / kColsumRows);
+  colsum_kernel<<<dim3(slabs, batch), dim3(32, 8), 0, st>>>(Z, z_bs, R, ncols, ldz, part);
+  VIHMC_LAUNCH_OK("colsum_kernel");
+  colsum_finish_kernel<<<batch, 128, 0, st>>>(part, slabs, ncols, out, out_bs);
+  VIHMC_LAUNCH_OK("colsum_finish_kernel");
+  return VIHMC_OK;
 }
 
 // fixed-order sum of per-tile partials: out[b] = sum_t part[b, t]  (one warp per batch row)
@@ -419,6 +445,10 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long f = splitk_scratch_floats(pl.b.dims[l], pl.b.in_of(l), (int)pl.P, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
+  if (pl.deeponet) {   // dBout = G Tout reduces over the P trunk points
+    const long long f = splitk_scratch_floats((int)pl.N, pl.K, (int)pl.P, 1);
+    pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
+  }
   pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
   // shared by every chain: pad map, trunk features, padded copy of the targets
   pl.shared_floats = pl.D + 64 + (pl.deeponet ? pl.P * 5 + 64 + pl.N * pl.Pp + 64 : 0);
@@ -500,10 +530,8 @@ static int stack_backward(const Stack& s, const float* input, long long R, const
     g.C = dWf + s.w_off[l]; g.c_bs = D; g.ldc = s.ldw[l];
     g.M = out; g.N = in; g.K = (int)R;
     if (int rc = launch_gemm<EPI_STORE>(g, Cb, st, scratch)) return rc;
-    if (s.has_bias[l]) {
-      colsum_kernel<<<dim3((out + 31) / 32, Cb), dim3(32, 8), 0, st>>>(dz_cur, R * out, R, out, out, dWf + s.b_off[l], D);
-      VIHMC_LAUNCH_OK("colsum_kernel");
-    }
+    if (s.has_bias[l])   // dz_other is free until the dX GEMM below writes it: it holds the slab partials
+      if (int rc = launch_colsum(dz_cur, R * out, R, out, out, dz_other, dWf + s.b_off[l], D, Cb, st)) return rc;
     if (l > 0) {
       // dz_prev[r,i] = (sum_o dz[r,o] W[o,i]) * act'(a_{l-1}[r,i])
       GemmArgs h{};
@@ -648,7 +676,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
         h.A = G; h.a_bs = N * Pp; h.a_sm = Pp; h.a_sk = 1;
         h.B = Tout; h.b_bs = P * K; h.b_sk = K; h.b_sn = 1;
         h.C = dz0; h.c_bs = N * K; h.ldc = K; h.M = (int)N; h.N = K; h.K = (int)P;
-        if (int rc = launch_gemm<EPI_STORE>(h, Cb, st)) return rc;
+        if (int rc = launch_gemm<EPI_STORE>(h, Cb, st, scratch)) return rc;
         if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
         // dTout[p,k] = sum_n G[n,p] Bout[n,k]
         GemmArgs t{};

@@ -277,7 +277,7 @@ __device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, lon
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
+__global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // swizzled MN-major tiles need 1 KB-aligned bases
   unsigned char* smem = smem_raw;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SMEM_BYTES - 128);
@@ -314,6 +314,8 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_m
   TileLoader lb{g.B + (long long)b * g.b_bs, g.b_sn, g.b_sk, g.N, g.K, n0, b_mode};
   const uint32_t idesc = kIdesc | (a_mode == LOAD_MNVEC ? 1u << 15 : 0u) | (b_mode == LOAD_MNVEC ? 1u << 16 : 0u);
 
+  // One k-tile of register prefetch.  (Two tiles ahead was measured slower: 120+ registers leave room for only two
+  // resident CTAs, and a third CTA parked in tcgen05.alloc is what hides the launch latency of the next tile.)
   const int nk = (g.K + BK - 1) / BK;
   float4 ra[2], rb[2];
   la.fetch(0, tid, ra);
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(GemmArgs g, int a_m
     float* trow = tile + (q * 32 + lane) * TILE_LD + half * (BN / 2);
 #pragma unroll 2
     for (int cc = 0; cc < BN / 2; cc += 8) {
+      if (n0 + half * (BN / 2) + cc >= g.N) break;   // columns past N (100-wide layers in a 128-wide tile) are never read
       uint32_t r[8], rc[8];
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + cc);
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
