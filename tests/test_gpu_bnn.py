@@ -304,3 +304,39 @@ def test_law_of_the_chain_matches_oracle_sampler():
     assert float(ratio.min()) > 0.6 and float(ratio.max()) < 1.6, ratio
     p = acc_gpu
     assert abs(np.mean(accs) - p) < 4 * np.sqrt(max(p * (1 - p), 0.01) / len(accs)) + 0.02
+
+
+_AB_SCRIPT = r"""
+import hashlib, sys
+sys.path[:0] = [{root!r}, {pkg!r}, {tests!r}]
+import numpy as np, torch
+import cases
+from vihmc import engine
+g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+h = hashlib.sha256()
+for name in ("d40_nll", "d141_nll", "d14_nll"):
+    case = cases.bnn_case(g, name)
+    spec = cases.bnn_spec(case)
+    logp, grad = engine.logp_grad(spec, torch.from_numpy(case["q"]))
+    h.update(logp.cpu().numpy().tobytes()); h.update(grad.cpu().numpy().tobytes())
+    q0 = torch.from_numpy(np.repeat(case["q"][:1], 37, axis=0))
+    res = engine.run_sampler([spec], q0, num_samples=5, num_steps=23, step_size=5e-4, burn=1, seed=11)
+    h.update(res.samples.numpy().tobytes()); h.update(res.hamiltonians.numpy().tobytes()); h.update(res.accepted.numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_specialised_evaluation_is_bit_identical_to_the_generic_one():
+    """The 1-W-W-1 tanh fast path (compile-time layout, register-resident activations, FFMA2) must reproduce the generic
+    evaluation bit for bit: log-posterior, gradient, samples, Hamiltonians and accept decisions, for three VI subsets."""
+    import os, subprocess, sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _AB_SCRIPT.format(root=root, pkg=os.path.join(root, "vi-hmc_b200"), tests=os.path.join(root, "tests"))
+    digests = []
+    for generic in ("0", "1"):
+        env = dict(os.environ, VIHMC_SMALL_GENERIC=generic)
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]

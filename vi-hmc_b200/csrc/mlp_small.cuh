@@ -28,19 +28,23 @@ namespace vihmc {
 constexpr int kMaxHidden = 4;
 
 #ifndef VIHMC_SMALL_MINBLOCKS
-#define VIHMC_SMALL_MINBLOCKS 6   // register budget of the small-MLP kernels: 65536 / (128 * minblocks)
+#define VIHMC_SMALL_MINBLOCKS 4   // register budget of the small-MLP kernels: 65536 / (128 * minblocks) = 128
 #endif
 
 struct SmallLayout {
-  // weight region (floats from the chain base): row-major [unit][row stride] tables, and for the
-  // hidden->hidden layers a transposed copy [input unit][WSW] used by the backward data pass
+  // Per-chain shared memory, in floats from the chain base: [weight tables | activation rows | per-coordinate state].
+  // The first two regions depend on (W, n_hidden, in_dim) only, so the specialised kernel gets their offsets as
+  // compile-time constants; the per-coordinate arrays (dp = d rounded up to 4 entries each) come last.
+  // weight region: row-major [unit][row stride] tables, and for the hidden->hidden layers a transposed copy
+  // [input unit][WSW] used by the backward data pass
   int wbase[kMaxHidden + 1], ws[kMaxHidden + 1], bbase[kMaxHidden + 1], tbase[kMaxHidden + 1];
   int w_total;
+  // activation region: rows of NCS floats, offsets relative to act_base
+  int act_base, xs, h, da, dz, dO, ones, act_total;
+  int NC, NCS;
   // per-coordinate state, each dp entries
-  int q, p, g, qf, pmu, piv, meta, wpos, wposT, red;
-  // activation region: rows of NCS floats
-  int act_base, xs, h, da, dz, dO, ones;
-  int NC, NCS, dp, total;
+  int coord_base, dp, q, p, g, qf, pmu, piv, meta, wpos, wposT, red;
+  int total;
 };
 
 struct SmallParams {
@@ -53,10 +57,10 @@ struct SmallParams {
   SmallLayout lay;
 };
 
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // W = padded hidden width the kernel is compiled for
-inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, long long /*N*/) {
+__host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d) {
   SmallLayout L{};
   const int WSW = round_up(W, 4);
   int off = 0;
@@ -71,6 +75,19 @@ inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, lon
     if (l >= 1 && l < n_hidden) off += W * WSW;
   }
   L.w_total = off;
+  L.NC = (32 / W) * 8;
+  L.NCS = L.NC + 4;   // +4: eight different rows land in eight different bank groups
+  L.act_base = off;
+  int a = 0;
+  L.xs = a; a += in_dim * L.NCS;
+  L.h = a; a += n_hidden * W * L.NCS;
+  L.da = a; a += n_hidden * W * L.NCS;
+  L.dz = a; a += n_hidden * W * L.NCS;
+  L.dO = a; a += L.NCS;
+  L.ones = a; a += L.NCS;
+  L.act_total = a;
+  off += a;
+  L.coord_base = off;
   L.dp = round_up((int)d, 4);
   L.q = off; off += L.dp;
   L.p = off; off += L.dp;
@@ -82,17 +99,7 @@ inline SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, lon
   L.wpos = off; off += L.dp;
   L.wposT = off; off += L.dp;
   L.red = off; off += 8;      // cross-warp reduction slots (two warps per chain)
-  L.NC = (32 / W) * 8;
-  L.NCS = L.NC + 4;   // +4: eight different rows land in eight different bank groups
-  L.act_base = off;
-  int a = 0;
-  L.xs = a; a += in_dim * L.NCS;
-  L.h = a; a += n_hidden * W * L.NCS;
-  L.da = a; a += n_hidden * W * L.NCS;
-  L.dz = a; a += n_hidden * W * L.NCS;
-  L.dO = a; a += L.NCS;
-  L.ones = a; a += L.NCS;
-  L.total = off + a;
+  L.total = off;
   return L;
 }
 
@@ -208,6 +215,48 @@ __device__ __forceinline__ void dot_rows(const float* wrow, const float* rows, f
   }
 }
 
+// packed FP32 pairs (Blackwell FFMA2: one instruction, two IEEE fma.rn results -- bit-identical to two fmaf)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// dot_rows on packed pairs: acc[t] += sum_k wrow[k] * rows[k][t], t < 8 (same order of operations as dot_rows)
+template <int W, int NCS>
+__device__ __forceinline__ void dot_rows2(const float* wrow, const float* rows, float (&acc)[8]) {
+  constexpr int WSW = (W + 3) / 4 * 4;
+  float w[WSW];
+#pragma unroll
+  for (int k4 = 0; k4 < WSW / 4; ++k4) {
+    const float4 v = reinterpret_cast<const float4*>(wrow)[k4];
+    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+  }
+  unsigned long long a[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) a[m] = pack2(acc[2 * m], acc[2 * m + 1]);
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(rows + k * NCS);
+    const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(rows + k * NCS + 4);
+    const unsigned long long ww = pack2(w[k], w[k]);
+    a[0] = ffma2(ww, r0.x, a[0]);
+    a[1] = ffma2(ww, r0.y, a[1]);
+    a[2] = ffma2(ww, r1.x, a[2]);
+    a[3] = ffma2(ww, r1.y, a[3]);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) unpack2(a[m], acc[2 * m], acc[2 * m + 1]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // chain-level geometry: NW warps cooperate on one chain (NW = 1: everything is warp-synchronous;
 // NW = 2: twice the warps per SM to hide latency when the chain count is small, 4 points per lane,
@@ -267,7 +316,8 @@ template <int W, int NW>
 __device__ float chain_init(float* sm, const SmallParams& P, const float* q_row, int ct, int bar) {
   using C = Cfg<W, NW>;
   const SmallLayout& L = P.lay;
-  for (int i = ct; i < L.act_base; i += C::T) sm[i] = 0.0f;
+  for (int i = ct; i < L.w_total; i += C::T) sm[i] = 0.0f;                 // padded units and weight-row padding stay zero
+  for (int i = L.coord_base + ct; i < L.total; i += C::T) sm[i] = 0.0f;
   chain_sync<NW>(bar);
   if (P.frozen != nullptr) {
     for (long long f = ct; f < P.D; f += C::T) {
@@ -411,15 +461,17 @@ __device__ __forceinline__ void phase_b(float* sm, const SmallParams& P, int ct,
     const int m = meta[i];
     const float4* A = reinterpret_cast<const float4*>(act + (m >> 16));
     const float4* B = reinterpret_cast<const float4*>(act + (m & 0xffff));
-    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+    // two packed accumulators = four independent sums (x, y | z, w lanes of the float4 rows), FFMA2
+    unsigned long long acc01 = 0ull, acc23 = 0ull;
 #pragma unroll
     for (int c = 0; c < C::NC / 4; ++c) {
-      const float4 a = A[c], b = B[c];
-      acc0 = fmaf(a.x, b.x, acc0);
-      acc1 = fmaf(a.y, b.y, acc1);
-      acc2 = fmaf(a.z, b.z, acc2);
-      acc3 = fmaf(a.w, b.w, acc3);
+      const ulonglong2 a = reinterpret_cast<const ulonglong2*>(A)[c], b = reinterpret_cast<const ulonglong2*>(B)[c];
+      acc01 = ffma2(a.x, b.x, acc01);
+      acc23 = ffma2(a.y, b.y, acc23);
     }
+    float acc0, acc1, acc2, acc3;
+    unpack2(acc01, acc0, acc1);
+    unpack2(acc23, acc2, acc3);
     float gsum = (acc0 + acc1) + (acc2 + acc3);
     if (!first_chunk) gsum += sm[L.g + i];
     if (last_chunk) consume(i, gsum);
@@ -459,9 +511,94 @@ __device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallPara
 }
 
 // ------------------------------------------------------------------------------------------------
+// Specialised evaluation for the reference's BNN family (Neural_network/*/config.py: Linear(1,w) - tanh -
+// Linear(w,w) - tanh - Linear(w,1), all N data points in one chunk, one warp per chain).  Same arithmetic in the same
+// order as eval_likelihood_grad -- results are bit-identical (tested) -- but: weight / activation offsets are
+// compile-time constants (the layout of those regions depends on W only), the lane's inputs x and target y never
+// change and live in registers, the lane's own activations h0 / h1 stay in registers for the backward pass instead of
+// being re-read, and the dot products run on packed FFMA2.
+// ------------------------------------------------------------------------------------------------
+struct FastRegs {
+  float x[8];   // the lane's 8 inputs (unit mode)
+  float yv;     // the lane's target (point mode)
+};
+
+template <int W>
+__device__ __forceinline__ void fast_setup(const float* sm, int ct, float yv0, FastRegs& F) {
+  constexpr SmallLayout L = make_layout(W, 2, 1, 0);
+  constexpr int G = L.NC / 8;
+  const int c0 = ct < G * W ? (ct / W) * 8 : 0;
+  load8(sm + L.act_base + L.xs + c0, F.x);
+  F.yv = yv0;
+}
+
+template <int W, typename Consume>
+__device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F,
+                                           Consume&& consume) {
+  constexpr SmallLayout L = make_layout(W, 2, 1, 0);
+  constexpr int NC = L.NC, NCS = L.NCS, WSW = round_up(W, 4), G = NC / 8;
+  float* act = sm + L.act_base;
+  const bool unit = ct < G * W;                                   // lanes past the last (unit, point group) pair idle
+  const int j = unit ? ct % W : 0, c0 = unit ? (ct / W) * 8 : 0;
+  float h0[8], h1[8];
+  {  // layer 0: Linear(1, W)
+    const float w = sm[L.wbase[0] + j * L.ws[0]], b = sm[L.bbase[0] + j];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) h0[t] = tanh_sel(fmaf(w, F.x[t], b));
+    if (unit) store8(act + L.h + j * NCS + c0, h0);
+  }
+  __syncwarp();
+  {  // layer 1: Linear(W, W)
+    const float b = sm[L.bbase[1] + j];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) h1[t] = b;
+    dot_rows2<W, NCS>(sm + L.wbase[1] + j * WSW, act + L.h + c0, h1);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) h1[t] = tanh_sel(h1[t]);
+    if (unit) store8(act + L.h + (W + j) * NCS + c0, h1);
+  }
+  __syncwarp();
+  float ll_lane = 0.0f;
+  if (ct < NC) {  // output layer + Gaussian residual, lane = data point
+    const float* wo = sm + L.wbase[2];
+    const float* hl = act + L.h + W * NCS + ct;
+    float o = sm[L.bbase[2]];
+#pragma unroll
+    for (int k = 0; k < W; ++k) o = fmaf(wo[k], hl[k * NCS], o);
+    const bool valid = ct < P.N;
+    const float r = o - F.yv;
+    act[L.dO + ct] = valid ? -lik.prec * r : 0.0f;
+    if (valid) ll_lane = lik.ll_const - lik.half_prec * r * r;
+  }
+  __syncwarp();
+  {  // backward through the output layer and the second tanh
+    const float wo = sm[L.wbase[2] + j];
+    float dO[8], dz[8];
+    load8(act + L.dO + c0, dO);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dz[t] = wo * dO[t] * fmaf(-h1[t], h1[t], 1.0f);
+    if (unit) store8(act + L.dz + (W + j) * NCS + c0, dz);
+  }
+  __syncwarp();
+  {  // backward through Linear(W, W) (transposed table) and the first tanh
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
+    dot_rows2<W, NCS>(sm + L.tbase[1] + j * WSW, act + L.dz + W * NCS + c0, acc);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] *= fmaf(-h0[t], h0[t], 1.0f);
+    if (unit) store8(act + L.dz + j * NCS + c0, acc);
+  }
+  __syncwarp();
+  phase_b<W, 1>(sm, P, ct, true, true, consume);
+  __syncwarp();
+  return ll_lane;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel 1: log-posterior value + gradient for C chains (vihmc_logp_grad, MLP small path)
 // ------------------------------------------------------------------------------------------------
-template <int W, int NW>
+template <int W, int NW, bool FAST>
 __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C,
                                                                                          const float* __restrict__ q,
                                                                                          float* __restrict__ logp,
@@ -476,11 +613,19 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_gra
   const float yv0 = chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
   float lp_lane = 0.0f;
-  const float ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, [&](int i, float gl) {
+  auto consume = [&](int i, float gl) {
     const float dq = sm[L.q + i] - sm[L.pmu + i], iv = sm[L.piv + i];
     lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
     if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, gl);
-  });
+  };
+  float ll_lane;
+  if constexpr (FAST) {
+    FastRegs F;
+    fast_setup<W>(sm, ct, yv0, F);
+    ll_lane = eval_fast<W>(sm, P, lik, ct, F, consume);
+  } else {
+    ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, consume);
+  }
   const float total = chain_sum<NW>(fmaf(lp_lane, P.inv_prior_scale, ll_lane), sm + L.red, ct, bar) + P.prior_log_norm * P.inv_prior_scale;
   if (ct == 0) logp[chain] = total;
 }
@@ -528,7 +673,7 @@ struct SampleArgs {
   const float* inj_u;
 };
 
-template <int W, int NW>
+template <int W, int NW, bool FAST>
 __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr int T = Cfg<W, NW>::T;
@@ -542,6 +687,8 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
   const long long C = A.C;
   const float* q0 = A.q0 + chain * d;
   const float yv0 = chain_init<W, NW>(sm, P, q0, ct, bar);
+  FastRegs F;
+  if constexpr (FAST) fast_setup<W>(sm, ct, yv0, F);
   const int* wposv = reinterpret_cast<const int*>(sm + L.wpos);
   const int* wposTv = reinterpret_cast<const int*>(sm + L.wposT);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
@@ -593,7 +740,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
       const bool first = s == 0, last = s == nsteps;
       const float kick = first ? half_eps : eps;
       float lp_lane = 0.0f, ke_lane = 0.0f;
-      const float ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, [&](int i, float gl) {
+      auto consume = [&](int i, float gl) {
         const float qv0 = sm[L.q + i];
         const float dq = qv0 - sm[L.pmu + i], iv = sm[L.piv + i];
         lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
@@ -611,7 +758,10 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
           if (wt >= 0) sm[wt] = qv;
         }
         sm[L.p + i] = pv;
-      });
+      };
+      float ll_lane;
+      if constexpr (FAST) ll_lane = eval_fast<W>(sm, P, lik, ct, F, consume);
+      else ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, consume);
       if (first || last) {
         const float lp = chain_sum<NW>(fmaf(lp_lane, P.inv_prior_scale, ll_lane), red, ct, bar) + log_norm;
         if (first) logp0 = lp;
@@ -683,6 +833,7 @@ enum SmallOp { kOpLogpGrad = 0, kOpPredict = 1, kOpSample = 2 };
 
 struct SmallLaunch {
   int warps_per_chain, chains_per_block, blocks;
+  int fast;   // specialised 1-W-W-1 tanh single-chunk evaluation (eval_fast)
   size_t smem;
   long long C;
   const float* q;
@@ -698,11 +849,11 @@ static int set_smem(K kernel, size_t bytes) {
   return VIHMC_OK;
 }
 
-template <int W, int NW>
+template <int W, int NW, bool FAST>
 static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
   const int threads = a.chains_per_block * 32 * NW;
   if (op == kOpLogpGrad) {
-    auto k = mlp_small_logp_grad_kernel<W, NW>;
+    auto k = mlp_small_logp_grad_kernel<W, NW, FAST>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.logp, a.grad);
     VIHMC_LAUNCH_OK("mlp_small_logp_grad_kernel");
@@ -712,7 +863,7 @@ static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& 
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.out);
     VIHMC_LAUNCH_OK("mlp_small_predict_kernel");
   } else {
-    auto k = mlp_small_sample_kernel<W, NW>;
+    auto k = mlp_small_sample_kernel<W, NW, FAST>;
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.A);
     VIHMC_LAUNCH_OK("mlp_small_sample_kernel");
@@ -722,8 +873,9 @@ static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& 
 
 template <int W>
 static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
-  if (a.warps_per_chain == 2) return launch_small_wn<W, 2>(op, P, a, st);
-  return launch_small_wn<W, 1>(op, P, a, st);
+  if (a.warps_per_chain == 2) return launch_small_wn<W, 2, false>(op, P, a, st);
+  if (a.fast) return launch_small_wn<W, 1, true>(op, P, a, st);
+  return launch_small_wn<W, 1, false>(op, P, a, st);
 }
 
 }  // namespace vihmc
