@@ -120,13 +120,16 @@ __device__ __forceinline__ float act_fwd(int act, float z, float& dact) {
   }
 }
 
-// tanh(x) = sign(x) (1 - 2 / (exp(2|x|) + 1)) on ex2.approx / rcp.approx: 8 instructions, no branch.
+// tanh(x) = sign(x) (1 - 2 / (2^(|x| * 2 log2 e) + 1)) on ex2.approx / rcp.approx: 6 instructions (FMUL, MUFU.EX2, FADD,
+// MUFU.RCP, FFMA, LOP3), no branch; e = +inf for large |x| gives rcp = 0 and tanh = +-1 exactly.
 // Absolute error <= ~1.2e-7 (one ulp at 1.0) over the whole range -- the same as tanhf's large-|x|
 // branch; near 0 the RELATIVE error grows like 6e-8/|x|, which is harmless here because activations only
 // ever enter sums against O(1) terms (checked by the rtol-1e-5 parity tests against the reference).
 __device__ __forceinline__ float tanh_sel(float x) {
-  const float e = __expf(2.0f * fabsf(x));
-  return copysignf(fmaf(-2.0f, __fdividef(1.0f, e + 1.0f), 1.0f), x);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return copysignf(fmaf(-2.0f, r, 1.0f), x);
 }
 
 // Gaussian likelihood pieces (main_VI_HMC.py:132-136; GaussianNLLLoss clamps var at 1e-6, full=False)

@@ -29,7 +29,11 @@ bool mlp_small_supported(const vihmc_problem* p) {
   return (size_t)L.total * sizeof(float) <= 200u * 1024u;  // one chain must fit in one CTA's smem
 }
 
-static int fill_params(const vihmc_problem* p, SmallParams& P, int& W) {
+static int warps_per_chain_for(long long C);
+static bool fast_path_enabled();
+
+// allow_fast: the caller's kernel has a specialised variant (log-posterior/gradient and the sampler; not predict)
+static int fill_params(const vihmc_problem* p, SmallParams& P, int& W, long long C, bool allow_fast, int& fast) {
   if (!mlp_small_supported(p))
     return fail(VIHMC_ERR_UNSUPPORTED, "MLP outside the small-net kernel's range (<=4 hidden layers of width <=32, out_dim 1)");
   if (p->x == nullptr || p->y == nullptr) return fail(VIHMC_ERR_INVALID, "x and y must be device pointers");
@@ -57,7 +61,9 @@ static int fill_params(const vihmc_problem* p, SmallParams& P, int& W) {
   P.prior_sigma_scalar = p->prior_sigma_scalar; P.prior_log_norm = p->prior_log_norm;
   P.x = p->x; P.y = p->y; P.frozen = p->frozen; P.prior_mu = p->prior_mu; P.prior_sigma = p->prior_sigma;
   P.sens_ind = reinterpret_cast<const long long*>(p->sens_ind);
-  P.lay = make_layout(W, nh, p->in_a, p->d);
+  fast = allow_fast && fast_path_enabled() && warps_per_chain_for(C) == 1 && nh == 2 && p->in_a == 1 && p->act == VIHMC_ACT_TANH &&
+         p->N <= (32 / W) * 8;
+  P.lay = make_layout(W, nh, p->in_a, p->d, fast != 0);
   return VIHMC_OK;
 }
 
@@ -92,7 +98,7 @@ static void pick_geometry(const SmallParams& P, long long C, SmallLaunch& a) {
   const SmallLayout& L = P.lay;
   const size_t per_chain = (size_t)L.total * sizeof(float);
   const int nw = warps_per_chain_for(C);
-  a.fast = fast_path_enabled() && nw == 1 && P.n_hidden == 2 && P.in_dim == 1 && P.act == VIHMC_ACT_TANH && P.N <= L.NC;
+
   int cpb = 1;
   while (cpb * nw < 4 && C > (long long)148 * 24 * cpb && per_chain * (cpb * 2) <= 200u * 1024u) cpb *= 2;
   a.warps_per_chain = nw;
@@ -112,8 +118,8 @@ static int dispatch(int W, SmallOp op, const SmallParams& P, const SmallLaunch& 
 int mlp_small_logp_grad(const vihmc_problem* prob, long long C, const float* q, float* logp, float* grad, cudaStream_t st) {
   SmallParams P{};
   int W = 0;
-  if (int rc = fill_params(prob, P, W)) return rc;
   SmallLaunch a{};
+  if (int rc = fill_params(prob, P, W, C, true, a.fast)) return rc;
   pick_geometry(P, C, a);
   a.q = q; a.logp = logp; a.grad = grad;
   return dispatch(W, kOpLogpGrad, P, a, st);
@@ -122,8 +128,8 @@ int mlp_small_logp_grad(const vihmc_problem* prob, long long C, const float* q, 
 int mlp_small_predict(const vihmc_problem* prob, long long C, const float* q, float* out, cudaStream_t st) {
   SmallParams P{};
   int W = 0;
-  if (int rc = fill_params(prob, P, W)) return rc;
   SmallLaunch a{};
+  if (int rc = fill_params(prob, P, W, C, false, a.fast)) return rc;
   pick_geometry(P, C, a);
   a.q = q; a.out = out;
   return dispatch(W, kOpPredict, P, a, st);
@@ -133,8 +139,8 @@ int mlp_small_sample(const vihmc_problem* prob, const vihmc_sampler_cfg* cfg, lo
                      const vihmc_sampler_io* io, cudaStream_t st) {
   SmallParams P{};
   int W = 0;
-  if (int rc = fill_params(prob, P, W)) return rc;
   SmallLaunch a{};
+  if (int rc = fill_params(prob, P, W, C, true, a.fast)) return rc;
   pick_geometry(P, C, a);
   a.A.cfg = *cfg; a.A.C = C; a.A.q0 = q0; a.A.samples = samples;
   if (io != nullptr) {

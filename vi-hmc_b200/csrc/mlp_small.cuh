@@ -59,8 +59,13 @@ struct SmallParams {
 
 __host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// W = padded hidden width the kernel is compiled for
-__host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d) {
+// Activation row stride of the specialised path (eval_fast): rows of s = NCS/4 float4 with s odd (phase B reads whole rows of
+// different units: 8 rows then sit in 8 different bank groups) and s*jp + nq distinct mod 8 over every quarter warp of the
+// lane = (unit pair jp, point quad nq) mapping, so the float4 row stores are conflict-free (found by enumeration).
+__host__ __device__ constexpr int fast_ncs(int W) { return W == 10 ? 52 : W == 16 ? 20 : W == 32 ? 12 : ((32 / W) * 8 + 4); }
+
+// W = padded hidden width the kernel is compiled for; fast = layout of the specialised 1-W-W-1 tanh path
+__host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, bool fast = false) {
   SmallLayout L{};
   const int WSW = round_up(W, 4);
   int off = 0;
@@ -76,12 +81,12 @@ __host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int i
   }
   L.w_total = off;
   L.NC = (32 / W) * 8;
-  L.NCS = L.NC + 4;   // +4: eight different rows land in eight different bank groups
+  L.NCS = fast ? fast_ncs(W) : L.NC + 4;   // +4: eight different rows land in eight different bank groups
   L.act_base = off;
   int a = 0;
   L.xs = a; a += in_dim * L.NCS;
   L.h = a; a += n_hidden * W * L.NCS;
-  L.da = a; a += n_hidden * W * L.NCS;
+  L.da = a; a += fast ? 0 : n_hidden * W * L.NCS;   // act'(z) rows: only the sine activation stores them
   L.dz = a; a += n_hidden * W * L.NCS;
   L.dO = a; a += L.NCS;
   L.ones = a; a += L.NCS;
@@ -519,43 +524,99 @@ __device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallPara
 // being re-read, and the dot products run on packed FFMA2.
 // ------------------------------------------------------------------------------------------------
 struct FastRegs {
-  float x[8];   // the lane's 8 inputs (unit mode)
+  float x[4];   // the lane's 4 inputs (unit mode)
   float yv;     // the lane's target (point mode)
+};
+
+// Unit-mode lane geometry of the specialised path: lane = (unit pair jp, point quad nq), i.e. a 2 x 4 register tile.
+// Per reduction step a lane reads ONE float4 of activations for 8 FMAs (the 1 x 8 tile of the generic path reads two):
+// the kernel is bound by shared-memory wavefronts, and an LDS.128 costs four of them however many lanes share its data.
+template <int W>
+struct FastLane {
+  static constexpr int JP = W / 2, NQ = ((32 / W) * 8) / 4;
+  static_assert(W % 2 == 0 && JP * NQ <= 32, "unit-mode lanes exceed the warp");
+  bool unit;
+  int j0, n0;   // the lane's units are j0 and j0 + JP (weight rows 12 floats apart stay conflict-free over consecutive j0)
+  __device__ __forceinline__ explicit FastLane(int ct) : unit(ct < JP * NQ), j0(unit ? ct % JP : 0), n0(unit ? 4 * (ct / JP) : 0) {}
 };
 
 template <int W>
 __device__ __forceinline__ void fast_setup(const float* sm, int ct, float yv0, FastRegs& F) {
-  constexpr SmallLayout L = make_layout(W, 2, 1, 0);
-  constexpr int G = L.NC / 8;
-  const int c0 = ct < G * W ? (ct / W) * 8 : 0;
-  load8(sm + L.act_base + L.xs + c0, F.x);
+  constexpr SmallLayout L = make_layout(W, 2, 1, 0, true);
+  const FastLane<W> ln(ct);
+  load8(sm + L.act_base + L.xs + ln.n0, F.x);
   F.yv = yv0;
+}
+
+// acc[u][t] += sum_k wrow_u[k] * rows[k][t], u < 2, t < 4, on packed pairs; k ascending as in dot_rows.
+// wrows = row of the lane's first unit; the second unit's row is W/2 rows further
+template <int W, int NCS>
+__device__ __forceinline__ void dot_rows_2x4(const float* wrows, const float* rows, float (&acc)[2][4]) {
+  constexpr int WSW = (W + 3) / 4 * 4;
+  float w[2][WSW];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int k4 = 0; k4 < WSW / 4; ++k4) {
+      const float4 v = reinterpret_cast<const float4*>(wrows + u * (W / 2) * WSW)[k4];
+      w[u][4 * k4] = v.x; w[u][4 * k4 + 1] = v.y; w[u][4 * k4 + 2] = v.z; w[u][4 * k4 + 3] = v.w;
+    }
+  unsigned long long a[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    a[u][0] = pack2(acc[u][0], acc[u][1]);
+    a[u][1] = pack2(acc[u][2], acc[u][3]);
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(rows + k * NCS);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long ww = pack2(w[u][k], w[u][k]);
+      a[u][0] = ffma2(ww, r.x, a[u][0]);
+      a[u][1] = ffma2(ww, r.y, a[u][1]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    unpack2(a[u][0], acc[u][0], acc[u][1]);
+    unpack2(a[u][1], acc[u][2], acc[u][3]);
+  }
 }
 
 template <int W, typename Consume>
 __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F,
                                            Consume&& consume) {
-  constexpr SmallLayout L = make_layout(W, 2, 1, 0);
-  constexpr int NC = L.NC, NCS = L.NCS, WSW = round_up(W, 4), G = NC / 8;
+  constexpr SmallLayout L = make_layout(W, 2, 1, 0, true);
+  constexpr int NC = L.NC, NCS = L.NCS, WSW = round_up(W, 4), JP = W / 2;
   float* act = sm + L.act_base;
-  const bool unit = ct < G * W;                                   // lanes past the last (unit, point group) pair idle
-  const int j = unit ? ct % W : 0, c0 = unit ? (ct / W) * 8 : 0;
-  float h0[8], h1[8];
+  const FastLane<W> ln(ct);
+  const int j0 = ln.j0, n0 = ln.n0;
+  float h0[2][4], h1[2][4];
   {  // layer 0: Linear(1, W)
-    const float w = sm[L.wbase[0] + j * L.ws[0]], b = sm[L.bbase[0] + j];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) h0[t] = tanh_sel(fmaf(w, F.x[t], b));
-    if (unit) store8(act + L.h + j * NCS + c0, h0);
+    for (int u = 0; u < 2; ++u) {
+      const float w = sm[L.wbase[0] + (j0 + u * JP) * L.ws[0]], b = sm[L.bbase[0] + j0 + u * JP];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h0[u][t] = tanh_sel(fmaf(w, F.x[t], b));
+      if (ln.unit) store8(act + L.h + (j0 + u * JP) * NCS + n0, h0[u]);
+    }
   }
   __syncwarp();
   {  // layer 1: Linear(W, W)
-    const float b = sm[L.bbase[1] + j];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) h1[t] = b;
-    dot_rows2<W, NCS>(sm + L.wbase[1] + j * WSW, act + L.h + c0, h1);
+    for (int u = 0; u < 2; ++u) {
+      const float b = sm[L.bbase[1] + j0 + u * JP];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) h1[t] = tanh_sel(h1[t]);
-    if (unit) store8(act + L.h + (W + j) * NCS + c0, h1);
+      for (int t = 0; t < 4; ++t) h1[u][t] = b;
+    }
+    dot_rows_2x4<W, NCS>(sm + L.wbase[1] + j0 * WSW, act + L.h + n0, h1);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h1[u][t] = tanh_sel(h1[u][t]);
+      if (ln.unit) store8(act + L.h + (W + j0 + u * JP) * NCS + n0, h1[u]);
+    }
   }
   __syncwarp();
   float ll_lane = 0.0f;
@@ -572,22 +633,31 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
   }
   __syncwarp();
   {  // backward through the output layer and the second tanh
-    const float wo = sm[L.wbase[2] + j];
-    float dO[8], dz[8];
-    load8(act + L.dO + c0, dO);
+    float dO[4];
+    load8(act + L.dO + n0, dO);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) dz[t] = wo * dO[t] * fmaf(-h1[t], h1[t], 1.0f);
-    if (unit) store8(act + L.dz + (W + j) * NCS + c0, dz);
+    for (int u = 0; u < 2; ++u) {
+      const float wo = sm[L.wbase[2] + j0 + u * JP];
+      float dz[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dz[t] = wo * dO[t] * fmaf(-h1[u][t], h1[u][t], 1.0f);
+      if (ln.unit) store8(act + L.dz + (W + j0 + u * JP) * NCS + n0, dz);
+    }
   }
   __syncwarp();
   {  // backward through Linear(W, W) (transposed table) and the first tanh
-    float acc[8];
+    float acc[2][4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
-    dot_rows2<W, NCS>(sm + L.tbase[1] + j * WSW, act + L.dz + W * NCS + c0, acc);
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[t] *= fmaf(-h0[t], h0[t], 1.0f);
-    if (unit) store8(act + L.dz + j * NCS + c0, acc);
+      for (int t = 0; t < 4; ++t) acc[u][t] = 0.0f;
+    dot_rows_2x4<W, NCS>(sm + L.tbase[1] + j0 * WSW, act + L.dz + W * NCS + n0, acc);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[u][t] *= fmaf(-h0[u][t], h0[u][t], 1.0f);
+      if (ln.unit) store8(act + L.dz + (j0 + u * JP) * NCS + n0, acc[u]);
+    }
   }
   __syncwarp();
   phase_b<W, 1>(sm, P, ct, true, true, consume);
