@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const long long* __res
 // H1 (and therefore accept/reject) depend on arrival order, so instead each CTA writes its partial to
 // ke_part[c, blockIdx.x] and the accept kernel sums the few partials in fixed order.
 // ---------------------------------------------------------------------------------------------
+// position of a float pointer inside its 16-byte group (0 = aligned)
+__device__ __forceinline__ int align_phase(const float* p) { return (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3u); }
+
 constexpr int kUpdVec = 4;                 // float4 per thread per iteration
 constexpr int kUpdSlab = kThreads * kUpdVec * 4;  // coordinates per CTA
 
@@ -112,37 +115,34 @@ __global__ void __launch_bounds__(kThreads) leapfrog_update_kernel(float* __rest
   const long long lo = (long long)blockIdx.x * kUpdSlab;
   const long long hi = lo + kUpdSlab < d ? lo + kUpdSlab : d;
   float ke = 0.0f;
-  const bool vec_ok = ((row % 4) == 0);
-  if (vec_ok) {
-    const long long hi4 = lo + ((hi - lo) / 4) * 4;
-    for (long long i = lo + 4LL * threadIdx.x; i < hi4; i += 4LL * kThreads) {
-      float4 qv = *reinterpret_cast<const float4*>(q + row + i);
-      float4 pv = *reinterpret_cast<const float4*>(p + row + i);
-      const float4 gv = *reinterpret_cast<const float4*>(g + row + i);
-      pv.x = axpy_unfused(ck, gv.x, pv.x); pv.y = axpy_unfused(ck, gv.y, pv.y);
-      pv.z = axpy_unfused(ck, gv.z, pv.z); pv.w = axpy_unfused(ck, gv.w, pv.w);
-      if (drift != 0.0f) {
-        qv.x = axpy_unfused(cd, pv.x, qv.x); qv.y = axpy_unfused(cd, pv.y, qv.y);
-        qv.z = axpy_unfused(cd, pv.z, qv.z); qv.w = axpy_unfused(cd, pv.w, qv.w);
-        *reinterpret_cast<float4*>(q + row + i) = qv;
-      }
-      *reinterpret_cast<float4*>(p + row + i) = pv;
-      ke = fmaf(pv.x, pv.x, ke); ke = fmaf(pv.y, pv.y, ke); ke = fmaf(pv.z, pv.z, ke); ke = fmaf(pv.w, pv.w, ke);
+  auto scalar = [&](long long i) {
+    const float pv = axpy_unfused(ck, g[row + i], p[row + i]);
+    if (drift != 0.0f) q[row + i] = axpy_unfused(cd, pv, q[row + i]);
+    p[row + i] = pv;
+    ke = fmaf(pv, pv, ke);
+  };
+  // d is odd for the reference's nets (172 401), so rows start at any alignment: peel to the first 16-byte boundary of
+  // this slab, stream float4, finish the tail.  Needs q, p, g to share their alignment phase (else: all scalar).
+  const int ph = align_phase(q + row + lo);
+  long long a0 = (ph == align_phase(p + row + lo) && ph == align_phase(g + row + lo)) ? lo + ((4 - ph) & 3) : hi;
+  if (a0 > hi) a0 = hi;
+  const long long hi4 = a0 + ((hi - a0) / 4) * 4;
+  for (long long i = lo + threadIdx.x; i < a0; i += kThreads) scalar(i);
+  for (long long i = a0 + 4LL * threadIdx.x; i < hi4; i += 4LL * kThreads) {
+    float4 qv = *reinterpret_cast<const float4*>(q + row + i);
+    float4 pv = *reinterpret_cast<const float4*>(p + row + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + row + i);
+    pv.x = axpy_unfused(ck, gv.x, pv.x); pv.y = axpy_unfused(ck, gv.y, pv.y);
+    pv.z = axpy_unfused(ck, gv.z, pv.z); pv.w = axpy_unfused(ck, gv.w, pv.w);
+    if (drift != 0.0f) {
+      qv.x = axpy_unfused(cd, pv.x, qv.x); qv.y = axpy_unfused(cd, pv.y, qv.y);
+      qv.z = axpy_unfused(cd, pv.z, qv.z); qv.w = axpy_unfused(cd, pv.w, qv.w);
+      *reinterpret_cast<float4*>(q + row + i) = qv;
     }
-    for (long long i = hi4 + threadIdx.x; i < hi; i += kThreads) {
-      const float pv = axpy_unfused(ck, g[row + i], p[row + i]);
-      if (drift != 0.0f) q[row + i] = axpy_unfused(cd, pv, q[row + i]);
-      p[row + i] = pv;
-      ke = fmaf(pv, pv, ke);
-    }
-  } else {
-    for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
-      const float pv = axpy_unfused(ck, g[row + i], p[row + i]);
-      if (drift != 0.0f) q[row + i] = axpy_unfused(cd, pv, q[row + i]);
-      p[row + i] = pv;
-      ke = fmaf(pv, pv, ke);
-    }
+    *reinterpret_cast<float4*>(p + row + i) = pv;
+    ke = fmaf(pv.x, pv.x, ke); ke = fmaf(pv.y, pv.y, ke); ke = fmaf(pv.z, pv.z, ke); ke = fmaf(pv.w, pv.w, ke);
   }
+  for (long long i = hi4 + threadIdx.x; i < hi; i += kThreads) scalar(i);
   if (ke_part != nullptr) {
     __shared__ float red[kThreads / 32];
     ke = warp_sum(ke);
@@ -206,12 +206,27 @@ __global__ void __launch_bounds__(kThreads) mh_accept_kernel(const float* __rest
   }
   const long long lo = (long long)blockIdx.x * kUpdSlab;
   const long long hi = lo + kUpdSlab < d ? lo + kUpdSlab : d;
-  for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
-    const float v = acc ? q_prop[row + i] : q_fb[row + i];
+  const float* __restrict__ src = acc ? q_prop : q_fb;   // accepted: proposal -> current, fallback, stored; rejected: fallback -> ...
+  auto scalar = [&](long long i) {
+    const float v = src[row + i];
     q_cur[row + i] = v;
     if (acc) q_fb[row + i] = v;
     if (store) stored[row + i] = v;
+  };
+  const int ph = align_phase(src + row + lo);
+  const bool same = ph == align_phase(q_cur + row + lo) && (!acc || ph == align_phase(q_fb + row + lo)) &&
+                    (!store || ph == align_phase(stored + row + lo));
+  long long a0 = same ? lo + ((4 - ph) & 3) : hi;
+  if (a0 > hi) a0 = hi;
+  const long long hi4 = a0 + ((hi - a0) / 4) * 4;
+  for (long long i = lo + threadIdx.x; i < a0; i += kThreads) scalar(i);
+  for (long long i = a0 + 4LL * threadIdx.x; i < hi4; i += 4LL * kThreads) {
+    const float4 v = *reinterpret_cast<const float4*>(src + row + i);
+    *reinterpret_cast<float4*>(q_cur + row + i) = v;
+    if (acc) *reinterpret_cast<float4*>(q_fb + row + i) = v;
+    if (store) *reinterpret_cast<float4*>(stored + row + i) = v;
   }
+  for (long long i = hi4 + threadIdx.x; i < hi; i += kThreads) scalar(i);
 }
 
 // ---------------------------------------------------------------------------------------------

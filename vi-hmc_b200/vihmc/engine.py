@@ -249,8 +249,17 @@ def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: 
         _lib.check(rc)
     res = SampleResult(samples, acc, ham, lp, eps, grad_evals_per_chain=evals, gpu_launches=launches)
     if to_host:
-        host = lambda t: None if t is None else t.cpu()
-        res = SampleResult(host(samples), host(acc), host(ham), host(lp), host(eps), evals, launches)
+        # device -> pinned host buffers (torch's caching host allocator reuses them across calls), all copies queued on the
+        # sampler's stream behind the kernel, one synchronisation at the end
+        def host(t):
+            if t is None:
+                return None
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+        with torch.cuda.device(dev):
+            res = SampleResult(host(samples), host(acc), host(ham), host(lp), host(eps), evals, launches)
+            torch.cuda.current_stream(dev).synchronize()
     return res
 
 
