@@ -136,54 +136,61 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 
 enum LoadMode { LOAD_SCALAR = 0, LOAD_KVEC = 1, LOAD_MNVEC = 2 };
 
-// One operand tile: rows [r0, r0+128) x k [k0, k0+16).  Element (r, k) lives at base + r*s_r + k*s_k.
-//   K-major modes: a warp instruction covers one 8-row group x 4 chunks: lane -> (row r8 = lane%8, chunk = lane/8),
-//     which makes the 16-byte shared-memory stores conflict-free and reads 64 contiguous bytes per row.
-//   MNVEC: a thread's float4 is 4 consecutive rows at one k; (warp, i) -> atom, lane -> (k row, 4-row block), see fetch().
+// One operand tile: rows [r0, r0+128) x k [kt*16, kt*16+16).  Element (r, k) lives at base + r*s_r + k*s_k.
+//   K-major modes: a warp instruction covers one 8-row group x 4 chunks: lane -> (row r8 = lane%8, chunk = lane/8).
+//   MNVEC: a thread's float4 is 4 consecutive rows at one k; (warp, i) -> atom, lane -> (k row, 4-row block).
 struct TileLoader {
-  const float* base;
-  long long s_r, s_k;
-  int R, K, r0;
-  int mode;
-  __device__ __forceinline__ void fetch(int k0, int tid, float4 (&v)[2]) const {
+  // Everything that does not depend on the k-tile is computed once per thread: the pointer of the thread's two float4
+  // at k-tile 0 (null when its rows are outside the matrix), how many of a float4's rows are inside (MNVEC), and the k
+  // offset inside a tile.  fetch(kt) then costs one pointer add and one k-bound test per float4.
+  const float* p[2];
+  long long s_k, step;   // element stride along K; pointer advance per k-tile
+  int koff[2], nrow[2];
+  int K, mode;
+  __device__ __forceinline__ void init(const float* base, long long s_r, long long sk, int R, int K_, int r0, int mode_, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
-    if (mode == LOAD_MNVEC) {
-      // (warp, i) -> one atom: 4 k-rows x 32 rows; lane -> (k row lane%4, 4-row block lane/4): a k-row is 128 contiguous bytes
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int atom = warp * 2 + i;   // mn atom = atom % 4, k atom = atom / 4
-        const int k = k0 + (atom >> 2) * 4 + (lane & 3);
-        const int r = r0 + (atom & 3) * 32 + (lane >> 2) * 4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < K && r < R) {
-          const float* p = base + r + (long long)k * s_k;
-          if (r + 3 < R) {
-            x = __ldg(reinterpret_cast<const float4*>(p));
-          } else {
-            x.x = __ldg(p);
-            if (r + 1 < R) x.y = __ldg(p + 1);
-            if (r + 2 < R) x.z = __ldg(p + 2);
-          }
-        }
-        v[i] = x;
-      }
-      return;
-    }
-    const int r8 = lane & 7, ch = lane >> 3;
+    s_k = sk; step = (long long)BK * sk; K = K_; mode = mode_;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int r = r0 + (i * 8 + warp) * 8 + r8;
-      const int k = k0 + ch * 4;
+      int r;
+      if (mode == LOAD_MNVEC) {
+        // (warp, i) -> one atom: 4 k-rows x 32 rows; lane -> (k row lane%4, 4-row block lane/4): a k-row is 128 contiguous bytes
+        const int atom = warp * 2 + i;   // mn atom = atom % 4, k atom = atom / 4
+        koff[i] = (atom >> 2) * 4 + (lane & 3);
+        r = r0 + (atom & 3) * 32 + (lane >> 2) * 4;
+        nrow[i] = R - r < 4 ? (R - r > 0 ? R - r : 0) : 4;
+        p[i] = base + r + (long long)koff[i] * sk;
+      } else {
+        // lane -> (row r8 = lane%8, chunk = lane/8): 16-byte stores of a quarter warp are conflict-free, 64 contiguous bytes per row
+        koff[i] = (lane >> 3) * 4;
+        r = r0 + (i * 8 + warp) * 8 + (lane & 7);
+        nrow[i] = r < R ? 1 : 0;
+        p[i] = base + (long long)r * s_r + (long long)koff[i] * sk;
+      }
+    }
+  }
+  __device__ __forceinline__ void fetch(int kt, float4 (&v)[2]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < R && k < K) {
-        const float* p = base + (long long)r * s_r + (long long)k * s_k;
-        if (mode == LOAD_KVEC && k + 3 < K) {
-          x = __ldg(reinterpret_cast<const float4*>(p));
+      const int k = kt * BK + koff[i];
+      const float* q = p[i] + (long long)kt * step;
+      if (nrow[i] > 0 && k < K) {
+        if (mode == LOAD_MNVEC) {
+          if (nrow[i] == 4) {
+            x = __ldg(reinterpret_cast<const float4*>(q));
+          } else {
+            x.x = __ldg(q);
+            if (nrow[i] > 1) x.y = __ldg(q + 1);
+            if (nrow[i] > 2) x.z = __ldg(q + 2);
+          }
+        } else if (mode == LOAD_KVEC && k + 3 < K) {
+          x = __ldg(reinterpret_cast<const float4*>(q));
         } else {
-          x.x = __ldg(p);
-          if (k + 1 < K) x.y = __ldg(p + s_k);
-          if (k + 2 < K) x.z = __ldg(p + 2 * s_k);
-          if (k + 3 < K) x.w = __ldg(p + 3 * s_k);
+          x.x = __ldg(q);
+          if (k + 1 < K) x.y = __ldg(q + s_k);
+          if (k + 2 < K) x.z = __ldg(q + 2 * s_k);
+          if (k + 3 < K) x.w = __ldg(q + 3 * s_k);
         }
       }
       v[i] = x;
@@ -217,57 +224,89 @@ __device__ __forceinline__ uint64_t step_desc(uint32_t tile_saddr, int mode, int
 }
 
 
-// Phase-2 epilogue of one staged row: applies the fused epilogue to tile_row[0..BN) and writes C.  With `vec`
-// (C rows 16-byte aligned, N % 4 == 0) every lane handles 4 consecutive columns with one LDS.128 / STG.128
-// (one warp instruction = one 512-byte row); otherwise lane + 32*j columns (128 contiguous bytes each).
-template <int EPI>
-__device__ __forceinline__ void epilogue_row(const GemmArgs& g, const float* tile_row, float* crow, const float* arow,
-                                             const float* biasb, int n0, int lane, bool vec, bool vec_aux, float bias0,
-                                             float& ll_acc, float& g_acc) {
+// Phase-2 epilogue of the staged tile: warp w owns rows w, w+8, ...; applies the fused epilogue and writes C.  With
+// `vec` (C rows 16-byte aligned, N % 4 == 0 or padded rows) every lane handles 4 consecutive columns with one
+// LDS.128 / STG.128 (one warp instruction = one 512-byte row); otherwise lane + 32*j columns (128 contiguous bytes
+// each).  ACT is a template parameter so the activation is chosen once per kernel, not per element; the bias of a
+// lane's columns is loaded once, row pointers advance by constant strides.
+enum { ACT_NONE = -1 };
+
+struct EpiCtx {
+  const float* tile;       // staged accumulators [BM][TILE_LD]
+  float* crow;             // C + (m0 + warp) * ldc + n0
+  const float* arow;       // aux + (m0 + warp) * ld_aux + n0 (or null)
+  const float* biasb;      // bias of this batch (EPI_BIAS_ACT)
+  long long c_step, a_step;   // 8 rows of C / aux
+  int rows, n0, N, lane, warp;
+  bool vec, vec_aux;
+  float bias0, ll_const, half_prec, prec;
+};
+
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_rows(const EpiCtx& e, float& ll_acc, float& g_acc) {
   auto apply = [&](float v, float bias_v, float aux_v) -> float {
     if (EPI == EPI_BIAS_ACT) {
       v += bias_v;
-      if (g.act == VIHMC_ACT_TANH) v = tanh_sel(v);   // 8 instructions, abs. error ~1.2e-7 (see common.cuh)
-      else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+      if (ACT == VIHMC_ACT_TANH) v = tanh_sel(v);   // 6 instructions, abs. error ~1.2e-7 (see common.cuh)
+      else if (ACT == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
     } else if (EPI == EPI_DACT) {
-      v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - aux_v * aux_v) : (aux_v > 0.0f ? 1.0f : 0.0f);
+      v *= (ACT == VIHMC_ACT_TANH) ? (1.0f - aux_v * aux_v) : (aux_v > 0.0f ? 1.0f : 0.0f);
     } else if (EPI == EPI_HEAD) {
-      const float res = v + bias0 - aux_v;
-      ll_acc += g.ll_const - g.half_prec * res * res;
-      v = -g.prec * res;
+      const float res = v + e.bias0 - aux_v;
+      ll_acc += e.ll_const - e.half_prec * res * res;
+      v = -e.prec * res;
       g_acc += v;
     }
     return v;
   };
-  if (vec) {
-    const int c = lane * 4;
-    if (n0 + c < g.N) {
-      const float4 v = *reinterpret_cast<const float4*>(tile_row + c);
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (EPI == EPI_BIAS_ACT) {
-        bv.x = __ldg(biasb + n0 + c); bv.y = __ldg(biasb + n0 + c + 1); bv.z = __ldg(biasb + n0 + c + 2); bv.w = __ldg(biasb + n0 + c + 3);
-      }
+  const float* trow = e.tile + e.warp * TILE_LD;
+  float* crow = e.crow;
+  const float* arow = e.arow;
+  if (e.vec) {
+    const int c = e.lane * 4;
+    const int nv = e.N - (e.n0 + c);   // valid columns of this lane's float4 (N % 4 != 0 only with padded rows)
+    if (nv <= 0) return;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI == EPI_BIAS_ACT) {
+      bv.x = __ldg(e.biasb + e.n0 + c);
+      if (nv > 1) bv.y = __ldg(e.biasb + e.n0 + c + 1);
+      if (nv > 2) bv.z = __ldg(e.biasb + e.n0 + c + 2);
+      if (nv > 3) bv.w = __ldg(e.biasb + e.n0 + c + 3);
+    }
+#pragma unroll 2
+    for (int r = e.warp; r < e.rows; r += THREADS / 32) {
+      const float4 v = *reinterpret_cast<const float4*>(trow + c);
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
       if (EPI == EPI_DACT || EPI == EPI_HEAD) {
-        if (vec_aux) av = __ldg(reinterpret_cast<const float4*>(arow + c));
+        if (e.vec_aux) av = __ldg(reinterpret_cast<const float4*>(arow + c));
         else { av.x = __ldg(arow + c); av.y = __ldg(arow + c + 1); av.z = __ldg(arow + c + 2); av.w = __ldg(arow + c + 3); }
       }
-      // N % 4 != 0 only with row_pad_ok: the float4 is in memory, the columns past N get zeros and no likelihood terms
-      const int nv = g.N - (n0 + c);
       float4 o;
       o.x = apply(v.x, bv.x, av.x);
       o.y = nv > 1 ? apply(v.y, bv.y, av.y) : 0.0f;
       o.z = nv > 2 ? apply(v.z, bv.z, av.z) : 0.0f;
       o.w = nv > 3 ? apply(v.w, bv.w, av.w) : 0.0f;
       *reinterpret_cast<float4*>(crow + c) = o;
+      trow += (THREADS / 32) * TILE_LD;
+      crow += e.c_step;
+      arow += e.a_step;
     }
   } else {
+    float bias_v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = lane + 32 * j;
-      if (n0 + c >= g.N) continue;
-      const float bias_v = (EPI == EPI_BIAS_ACT) ? __ldg(biasb + n0 + c) : 0.0f;
-      const float aux_v = (EPI == EPI_DACT || EPI == EPI_HEAD) ? __ldg(arow + c) : 0.0f;
-      crow[c] = apply(tile_row[c], bias_v, aux_v);
+    for (int j = 0; j < 4; ++j)
+      if (EPI == EPI_BIAS_ACT && e.n0 + e.lane + 32 * j < e.N) bias_v[j] = __ldg(e.biasb + e.n0 + e.lane + 32 * j);
+    for (int r = e.warp; r < e.rows; r += THREADS / 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = e.lane + 32 * j;
+        if (e.n0 + c >= e.N) continue;
+        const float aux_v = (EPI == EPI_DACT || EPI == EPI_HEAD) ? __ldg(arow + c) : 0.0f;
+        crow[c] = apply(trow[c], bias_v[j], aux_v);
+      }
+      trow += (THREADS / 32) * TILE_LD;
+      crow += e.c_step;
+      arow += e.a_step;
     }
   }
 }
@@ -310,16 +349,17 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
 
-  TileLoader la{g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_mode};
-  TileLoader lb{g.B + (long long)b * g.b_bs, g.b_sn, g.b_sk, g.N, g.K, n0, b_mode};
+  TileLoader la, lb;
+  la.init(g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_mode, tid);
+  lb.init(g.B + (long long)b * g.b_bs, g.b_sn, g.b_sk, g.N, g.K, n0, b_mode, tid);
   const uint32_t idesc = kIdesc | (a_mode == LOAD_MNVEC ? 1u << 15 : 0u) | (b_mode == LOAD_MNVEC ? 1u << 16 : 0u);
 
   // One k-tile of register prefetch.  (Two tiles ahead was measured slower: 120+ registers leave room for only two
   // resident CTAs, and a third CTA parked in tcgen05.alloc is what hides the launch latency of the next tile.)
   const int nk = (g.K + BK - 1) / BK;
   float4 ra[2], rb[2];
-  la.fetch(0, tid, ra);
-  lb.fetch(0, tid, rb);
+  la.fetch(0, ra);
+  lb.fetch(0, rb);
   for (int kt = 0; kt < nk; ++kt) {
     const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
@@ -327,8 +367,8 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
     stash(st, st + TILE_BYTES, tid, a_mode, ra);
     stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, b_mode, rb);
     if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
-      la.fetch((kt + 1) * BK, tid, ra);
-      lb.fetch((kt + 1) * BK, tid, rb);
+      la.fetch(kt + 1, ra);
+      lb.fetch(kt + 1, rb);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
@@ -383,19 +423,26 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
     }
   }
   __syncthreads();
-  float* __restrict__ Cb = g.C + (long long)b * g.c_bs;
-  const float bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)b * g.bias_bs) : 0.0f;
-  const float* auxb = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs : nullptr;
-  const float* biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
-  const bool vec = rows_vec_ok(g.C, g.c_bs, g.ldc, g.N, g.row_pad_ok);
-  const bool vec_aux = auxb != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N, g.row_pad_ok);
+  EpiCtx e;
+  e.tile = tile;
+  e.crow = g.C + (long long)b * g.c_bs + (long long)(m0 + warp) * g.ldc + n0;
+  e.arow = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs + (long long)(m0 + warp) * g.ld_aux + n0 : nullptr;
+  e.biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
+  e.c_step = (long long)(THREADS / 32) * g.ldc;
+  e.a_step = (long long)(THREADS / 32) * g.ld_aux;
+  e.rows = g.M - m0 < BM ? g.M - m0 : BM;
+  e.n0 = n0; e.N = g.N; e.lane = lane; e.warp = warp;
+  e.vec = rows_vec_ok(g.C, g.c_bs, g.ldc, g.N, g.row_pad_ok);
+  e.vec_aux = e.arow != nullptr && rows_vec_ok(g.aux, g.aux_bs, g.ld_aux, g.N, g.row_pad_ok);
+  e.bias0 = (EPI == EPI_HEAD) ? __ldg(g.bias + (long long)b * g.bias_bs) : 0.0f;
+  e.ll_const = g.ll_const; e.half_prec = g.half_prec; e.prec = g.prec;
   float ll_acc = 0.0f, g_acc = 0.0f;
-#pragma unroll 2
-  for (int r = warp; r < BM; r += THREADS / 32) {
-    const int m = m0 + r;
-    if (m >= g.M) break;
-    epilogue_row<EPI>(g, tile + r * TILE_LD, Cb + (long long)m * g.ldc + n0, auxb ? auxb + (long long)m * g.ld_aux + n0 : nullptr,
-                      biasb, n0, lane, vec, vec_aux, bias0, ll_acc, g_acc);
+  if (EPI == EPI_BIAS_ACT || EPI == EPI_DACT) {
+    if (g.act == VIHMC_ACT_TANH) epilogue_rows<EPI, VIHMC_ACT_TANH>(e, ll_acc, g_acc);
+    else if (g.act == VIHMC_ACT_RELU) epilogue_rows<EPI, VIHMC_ACT_RELU>(e, ll_acc, g_acc);
+    else epilogue_rows<EPI, ACT_NONE>(e, ll_acc, g_acc);
+  } else {
+    epilogue_rows<EPI, ACT_NONE>(e, ll_acc, g_acc);
   }
   if (EPI == EPI_HEAD) {
     float* red = reinterpret_cast<float*>(smem);
