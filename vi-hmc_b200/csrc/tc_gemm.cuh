@@ -145,7 +145,7 @@ struct TileLoader {
   // offset inside a tile.  fetch(kt) then costs one pointer add and one k-bound test per float4.
   const float* p[2];
   long long s_k, step;   // element stride along K; pointer advance per k-tile
-  int koff[2], nrow[2];
+  int koff[2], nrow[2], soff[2];   // soff: byte offset of the float4 inside the staged tile
   int K, mode;
   __device__ __forceinline__ void init(const float* base, long long s_r, long long sk, int R, int K_, int r0, int mode_, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
@@ -160,12 +160,16 @@ struct TileLoader {
         r = r0 + (atom & 3) * 32 + (lane >> 2) * 4;
         nrow[i] = R - r < 4 ? (R - r > 0 ? R - r : 0) : 4;
         p[i] = base + r + (long long)koff[i] * sk;
+        // a quarter warp (4 k-rows x 2 half chunks) covers 8 distinct 16-byte bank groups: conflict-free
+        const int k4 = lane & 3;
+        soff[i] = (atom & 3) * MN_LBO + (atom >> 2) * MN_SBO + k4 * 128 + (((lane >> 3) ^ k4) * 32) + ((lane >> 2) & 1) * 16;
       } else {
         // lane -> (row r8 = lane%8, chunk = lane/8): 16-byte stores of a quarter warp are conflict-free, 64 contiguous bytes per row
         koff[i] = (lane >> 3) * 4;
         r = r0 + (i * 8 + warp) * 8 + (lane & 7);
         nrow[i] = r < R ? 1 : 0;
         p[i] = base + (long long)r * s_r + (long long)koff[i] * sk;
+        soff[i] = (i * 8 + warp) * SBO + (lane >> 3) * LBO + (lane & 7) * 16;
       }
     }
   }
@@ -198,22 +202,13 @@ struct TileLoader {
   }
 };
 
-__device__ __forceinline__ void stash(unsigned char* hi_tile, unsigned char* lo_tile, int tid, int mode, const float4 (&v)[2]) {
-  const int lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void stash(unsigned char* hi_tile, unsigned char* lo_tile, const TileLoader& ld, const float4 (&v)[2]) {
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    int off;
-    if (mode == LOAD_MNVEC) {
-      // a quarter warp (4 k-rows x 2 half chunks) covers 8 distinct 16-byte bank groups: conflict-free
-      const int atom = warp * 2 + i, k4 = lane & 3;
-      off = (atom & 3) * MN_LBO + (atom >> 2) * MN_SBO + k4 * 128 + (((lane >> 3) ^ k4) * 32) + ((lane >> 2) & 1) * 16;
-    } else {
-      off = (i * 8 + warp) * SBO + (lane >> 3) * LBO + (lane & 7) * 16;
-    }
     float4 hi, lo;
     split4(v[i], hi, lo);
-    *reinterpret_cast<float4*>(hi_tile + off) = hi;
-    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    *reinterpret_cast<float4*>(hi_tile + ld.soff[i]) = hi;
+    *reinterpret_cast<float4*>(lo_tile + ld.soff[i]) = lo;
   }
 }
 
@@ -364,8 +359,8 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
     const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
     if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
-    stash(st, st + TILE_BYTES, tid, a_mode, ra);
-    stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, b_mode, rb);
+    stash(st, st + TILE_BYTES, la, ra);
+    stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rb);
     if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
       la.fetch(kt + 1, ra);
       lb.fetch(kt + 1, rb);
