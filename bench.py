@@ -210,6 +210,12 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
     # ---- device-timed: inputs resident in HBM, one persistent launch of `steps` iterations ----
     launch(warmup, seed=1)
     torch.cuda.synchronize()
+    # the sampler allocates its result tensors with torch.empty: put blocks of those sizes into torch's caching allocator
+    # now, so that no cudaMalloc (a host-side, millisecond-scale call) lands between the two timing events
+    warm = [torch.empty((steps, CHAINS_PER_GPU, D_SAMPLED), device=dev), torch.empty((steps, CHAINS_PER_GPU, 2), device=dev),
+            torch.empty((steps, CHAINS_PER_GPU), device=dev), torch.empty((steps, CHAINS_PER_GPU), dtype=torch.uint8, device=dev),
+            torch.empty(CHAINS_PER_GPU, device=dev)]
+    del warm
     flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
