@@ -189,6 +189,9 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the contract is ONE line on stdout: NCCL_DEBUG=VERSION (set on some boxes) prints its banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
