@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "fused_stack.cuh"
 
 namespace vihmc {
 
@@ -395,8 +396,50 @@ struct DensePlan {
   long long head_tiles, loss_tiles;
   // per-chain float counts
   long long act_a_floats, act_b_floats, per_chain_floats, scratch_per_chain;
+  long long img_floats;      // pre-split weight images of the fused trunk forward (0 when the trunk is not eligible)
   long long shared_floats;  // trunk features
 };
+
+// VIHMC_DENSE_NOFUSE=1 keeps every stack on the per-layer GEMMs (A/B baseline of the fused kernel)
+static bool fused_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("VIHMC_DENSE_NOFUSE");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on && tensor_cores_enabled();
+}
+
+// shapes fused_forward_kernel takes: every width a multiple of 4 and <= 104, narrow input, bias everywhere
+static bool fused_eligible(const Stack& s) {
+  if (!fused_enabled() || s.n_layers < 2 || s.in_dim > fused::MAX_IN0) return false;
+  for (int l = 0; l < s.n_layers; ++l)
+    if (s.dims[l] % 4 != 0 || s.dims[l] > fused::KPAD || !s.has_bias[l]) return false;
+  return true;
+}
+
+// forward of one stack in ONE kernel (fused_stack.cuh); img: Cb * (n_layers-1) * 2 * B_TILE bytes of scratch
+static int stack_forward_fused(const Stack& s, const float* input, long long R, const float* Wf, long long Dp, float* const* acts,
+                               int act, int Cb, float* img, cudaStream_t st) {
+  fused::ImgTable t{};
+  t.n = s.n_layers - 1;
+  for (int l = 1; l < s.n_layers; ++l) t.L[l - 1] = fused::ImgLayer{s.w_off[l], s.dims[l], s.in_of(l), s.ldw[l], 1};
+  fused::weight_image_kernel<<<dim3(t.n, Cb), 256, 0, st>>>(Wf, Dp, t, img);
+  VIHMC_LAUNCH_OK("weight_image_kernel");
+  fused::FusedFwdArgs a{};
+  a.input = input; a.in_dim = s.in_dim; a.Wf = Wf; a.Dp = Dp; a.w0_off = s.w_off[0]; a.ldw0 = s.ldw[0];
+  for (int l = 0; l < s.n_layers; ++l) { a.b_off[l] = s.b_off[l]; a.dims[l] = s.dims[l]; a.acts[l] = acts[l]; }
+  a.n_layers = s.n_layers; a.img = img; a.R = R; a.act = act;
+  const dim3 grid((unsigned)((R + tc::BM - 1) / tc::BM), Cb);
+  auto launch = [&](auto kernel) -> int {
+    VIHMC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::F_SMEM));
+    kernel<<<grid, fused::F_THREADS, fused::F_SMEM, st>>>(a);
+    return VIHMC_OK;
+  };
+  if (act == VIHMC_ACT_TANH) { if (int rc = launch(fused::fused_forward_kernel<VIHMC_ACT_TANH>)) return rc; }
+  else { if (int rc = launch(fused::fused_forward_kernel<VIHMC_ACT_RELU>)) return rc; }
+  VIHMC_LAUNCH_OK("fused_forward_kernel");
+  return VIHMC_OK;
+}
 
 static int make_plan(const vihmc_problem* p, DensePlan& pl) {
   pl.deeponet = p->model_kind == VIHMC_MODEL_DEEPONET;
@@ -449,7 +492,8 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long f = splitk_scratch_floats((int)pl.N, pl.K, (int)pl.P, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
-  pl.per_chain_floats = pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
+  pl.img_floats = (pl.deeponet && fused_eligible(pl.b)) ? (long long)(pl.b.n_layers - 1) * (2 * fused::B_TILE / 4) + 64 : 0;
+  pl.per_chain_floats = pl.img_floats + pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
   // shared by every chain: pad map, trunk features, padded copy of the targets
   pl.shared_floats = pl.D + 64 + (pl.deeponet ? pl.P * 5 + 64 + pl.N * pl.Pp + 64 : 0);
   return VIHMC_OK;
@@ -645,12 +689,18 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     float* loglik = bb.take(Cb);
     float* prior_part = bb.take((long long)Cb * ((d + kFinSlab - 1) / kFinSlab));
     float* scratch = pl.scratch_per_chain > 0 ? bb.take((long long)Cb * pl.scratch_per_chain) : nullptr;
+    float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
     const float* qb = q + c0 * d;
 
     if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st)) return rc;
     if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
-    if (pl.deeponet)
-      if (int rc = stack_forward(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
+    if (pl.deeponet) {
+      if (img != nullptr) {
+        if (int rc = stack_forward_fused(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, Cb, img, st)) return rc;
+      } else {
+        if (int rc = stack_forward(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
+      }
+    }
 
     if (pl.deeponet) {
       // head: O = Bout * Tout^T + b0 ; fused residual / loglik partials
@@ -761,9 +811,14 @@ int dense_predict(const vihmc_problem* p, long long C, const float* q, float* ou
     for (int l = 0; l < pl.a.n_layers; ++l) acts_a[l] = bb.take((long long)Cb * N * pl.a.dims[l]);
     for (int l = 0; l < pl.b.n_layers; ++l) acts_b[l] = bb.take((long long)Cb * P * pl.b.dims[l]);
     float* part = bb.take(2LL * Cb * pl.head_tiles);
+    float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
     if (int rc = scatter_padded(p, pl, sb.pad_map, q + c0 * d, Wf, Cb, st)) return rc;
     if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
-    if (int rc = stack_forward(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
+    if (img != nullptr) {
+      if (int rc = stack_forward_fused(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, Cb, img, st)) return rc;
+    } else {
+      if (int rc = stack_forward(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
+    }
     // O = Bout Tout^T + b0 through the HEAD epilogue with a zero target and prec = -1: C = -(-1) * (O - 0) = O
     GemmArgs g{};
     const int K = pl.K;

@@ -1,0 +1,250 @@
+// All layers of one fully-connected stack for a 128-row tile in ONE kernel (forward pass of the DeepONet trunk / branch).
+//
+// Restates Operator_network/VI_HMC/my_make_func.py:53-61 (branch) and :69-77 (trunk): x = act(linear(x, W_l, b_l)) for every
+// layer but the last, which has no activation.  The per-layer GEMM path (tc_gemm.cuh) moves every activation tile
+// HBM -> registers -> split -> shared memory again for the next layer and spends most of its issue slots doing so; here the
+// activations of a row tile never leave the SM between layers:
+//   * the tile's activations live in shared memory as the 3xTF32 hi / lo operand pair (K-major, no swizzle, whole K = 104);
+//   * layer l's weights arrive PRE-SPLIT in the same layout (weight_image_kernel builds the hi / lo images once per gradient
+//     evaluation) with ONE cp.async.bulk + mbarrier::complete_tx per layer, overlapped with the previous layer's epilogue;
+//   * one thread issues the 13 x 3 tcgen05.mma (M = 128, N = 112, K = 8) of a layer into TMEM (main + correction accumulators);
+//   * the epilogue reads TMEM with the lane = row mapping, adds the bias, applies the activation, splits the result and
+//     stores hi / lo straight into the operand tiles of the next layer (a quarter warp = 8 rows = 128 contiguous bytes:
+//     conflict-free); the fp32 activations the backward pass needs are written to HBM by a coalesced pass over the
+//     operand tiles (h = hi + lo, ~1 ulp from the unsplit value) that runs while the tensor core works on the next layer.
+// Shared memory: 2 x 52 KB (activations) + 2 x 45.5 KB (weights) = 195 KB: one CTA per SM, 512 threads (the epilogue is a
+// chain of TMEM load -> tanh -> split -> store latencies; 16 warps hide what 8 could not: measured 3.2 ms -> see profiles).
+// Eligibility (host side): every width a multiple of 4 and <= 104, input width <= 8 (the first layer runs on the FP32 pipes).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace vihmc {
+namespace fused {
+
+using tc::BM;
+constexpr int KPAD = 104, NPAD = 112;            // reduction / output widths the operand tiles are laid out for
+constexpr int KCH = KPAD / 4;                     // 16-byte chunks per row
+constexpr int RG_BYTES = KCH * 128;               // one 8-row group (the descriptors' SBO); LBO = 128
+constexpr int A_TILE = (BM / 8) * RG_BYTES;       // 53,248 B
+constexpr int B_TILE = (NPAD / 8) * RG_BYTES;     // 46,592 B
+constexpr int F_SMEM = 2 * A_TILE + 2 * B_TILE + 128;
+constexpr int F_THREADS = 512;                     // 16 warps: four per TMEM lane quarter, 32 accumulator columns each
+constexpr int MAX_IN0 = 8;                        // widest first-layer input handled by the FP32 first layer
+constexpr uint32_t kIdescF = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---- weight images ----
+// Operand element (n, k) of image l is W[n*ld_n + k*ld_k] at w_off inside the chain's padded weight vector
+// (forward: W[n][k]: ld_n = row stride, ld_k = 1).  Image = hi tile then lo tile, B_TILE bytes each, zero padded.
+struct ImgLayer { long long w_off; int n_rows, n_k, ld_n, ld_k; };
+struct ImgTable { int n; ImgLayer L[VIHMC_MAX_LAYERS]; };
+
+__global__ void __launch_bounds__(256) weight_image_kernel(const float* __restrict__ Wf, long long Dp, ImgTable t, float* __restrict__ img) {
+  const int l = blockIdx.x;
+  const long long c = blockIdx.y;
+  const ImgLayer L = t.L[l];
+  const float* __restrict__ W = Wf + c * Dp + L.w_off;
+  float* hi = img + (c * t.n + l) * (2 * B_TILE / 4);
+  float* lo = hi + B_TILE / 4;
+  for (int e = threadIdx.x; e < B_TILE / 4; e += blockDim.x) {
+    const int j = e & 3, r8 = (e >> 2) & 7, ch = (e >> 5) % KCH, rg = (e >> 5) / KCH;
+    const int n = rg * 8 + r8, k = ch * 4 + j;
+    float v = 0.0f;
+    if (n < L.n_rows && k < L.n_k) v = __ldg(W + (long long)n * L.ld_n + (long long)k * L.ld_k);
+    const float h = tc::rna_tf32(v);
+    hi[e] = h;
+    lo[e] = tc::rna_tf32(v - h);
+  }
+}
+
+struct FusedFwdArgs {
+  const float* input;                     // [R, in_dim], shared by every chain
+  int in_dim;
+  const float* Wf;                        // padded weights [Cb, Dp]: first-layer weights and all biases are read from here
+  long long Dp;
+  long long w0_off;
+  int ldw0;
+  long long b_off[VIHMC_MAX_LAYERS];
+  int dims[VIHMC_MAX_LAYERS];
+  int n_layers;
+  const float* img;                       // images of layers 1 .. n_layers-1: [Cb, n_layers-1, 2, B_TILE/4]
+  float* acts[VIHMC_MAX_LAYERS];          // acts[l]: [Cb, R, dims[l]]
+  long long R;
+  int act;                                // activation between layers (none after the last)
+};
+
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+  if (ACT == VIHMC_ACT_TANH) return tanh_sel(v);
+  if (ACT == VIHMC_ACT_RELU) return v > 0.0f ? v : 0.0f;
+  return v;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* A_hi = smem;
+  unsigned char* A_lo = smem + A_TILE;
+  unsigned char* B_hi = smem + 2 * A_TILE;          // the lo image follows contiguously, as in global memory
+  uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + 2 * A_TILE + 2 * B_TILE);
+  uint64_t* bar_mma = bar_b + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long c = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * BM;
+  const float* __restrict__ Wc = a.Wf + c * a.Dp;
+  const int n_img = a.n_layers - 1;
+
+  if (tid == 0) {
+    tc::mbar_init(bar_b, 1);
+    tc::mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // operand tiles start as zeros: the K padding (columns >= the layer width) must stay zero for every layer
+  for (int i = tid; i < 2 * A_TILE / 16; i += F_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  auto load_weights = [&](int l) {   // thread 0: one bulk copy of layer l's hi + lo images, completion on bar_b
+    const float* src = a.img + (c * n_img + (l - 1)) * (2 * B_TILE / 4);
+    const uint32_t bytes = 2u * B_TILE;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar_b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(B_hi)),
+                 "l"(src), "r"(bytes), "r"(tc::smem_u32(bar_b))
+                 : "memory");
+  };
+  if (tid == 0 && a.n_layers > 1) load_weights(1);
+
+  // ---- layer 0 on the FP32 pipes: warp -> row group, lane -> (row r8 = lane%8, chunks lane/8 + 4j) ----
+  {
+    const int r8 = lane & 7, cq = lane >> 3, rg = warp;
+    const int n0w = a.dims[0];
+    const long long grow = r0 + rg * 8 + r8;
+    float f[MAX_IN0];
+#pragma unroll
+    for (int k = 0; k < MAX_IN0; ++k) f[k] = (k < a.in_dim && grow < a.R) ? __ldg(a.input + grow * a.in_dim + k) : 0.0f;
+    for (int ch = cq; 4 * ch < n0w; ch += 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * ch + j;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < MAX_IN0; ++k)
+          if (k < a.in_dim) acc = fmaf(__ldg(Wc + a.w0_off + (long long)n * a.ldw0 + k), f[k], acc);
+        acc += __ldg(Wc + a.b_off[0] + n);
+        v[j] = a.n_layers > 1 ? activate<ACT>(acc) : acc;
+      }
+      float4 hi, lo;
+      tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+      const int off = rg * RG_BYTES + ch * 128 + r8 * 16;
+      *reinterpret_cast<float4*>(A_hi + off) = hi;
+      *reinterpret_cast<float4*>(A_lo + off) = lo;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  // coalesced write of the activations held in the operand tiles: acts[l][c, r0 + row, :] = hi + lo
+  auto store_acts = [&](int l) {
+    const int r8 = lane & 7, cq = lane >> 3, rg = warp;
+    const int nw = a.dims[l];
+    const long long grow = r0 + rg * 8 + r8;
+    if (grow >= a.R) return;
+    float* __restrict__ out = a.acts[l] + (c * a.R + grow) * nw + 4 * cq;
+    const unsigned char* ph = A_hi + rg * RG_BYTES + cq * 128 + r8 * 16;
+    for (int ch = cq; 4 * ch < nw; ch += 4) {
+      const float4 hi = *reinterpret_cast<const float4*>(ph);
+      const float4 lo = *reinterpret_cast<const float4*>(ph + A_TILE);
+      *reinterpret_cast<float4*>(out) = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+      ph += 4 * 128;
+      out += 16;
+    }
+  };
+
+  for (int l = 1; l < a.n_layers; ++l) {
+    const int K = a.dims[l - 1], N = a.dims[l];
+    const uint32_t ph = (uint32_t)(l - 1) & 1u;
+    if (tid == 0) {
+      tc::mbar_wait(bar_b, ph);   // this layer's weight images have landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = tc::smem_u32(A_hi), sb = tc::smem_u32(B_hi);
+      const int ksteps = (K + 7) / 8;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t ko = (uint32_t)ks * 256u;   // one K = 8 step = two 16-byte chunks, 128 B apart
+        const uint64_t a_hi = tc::make_desc(sa + ko, 128, RG_BYTES), a_lo = tc::make_desc(sa + A_TILE + ko, 128, RG_BYTES);
+        const uint64_t b_hi = tc::make_desc(sb + ko, 128, RG_BYTES), b_lo = tc::make_desc(sb + B_TILE + ko, 128, RG_BYTES);
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        tc::mma_tf32(tmem_d, a_hi, b_hi, kIdescF, acc);            // main product
+        tc::mma_tf32(tmem_d + 128, a_lo, b_hi, kIdescF, acc);      // corrections in their own accumulator (see tc_gemm.cuh)
+        tc::mma_tf32(tmem_d + 128, a_hi, b_lo, kIdescF, 1u);
+      }
+      tc::mma_commit(bar_mma);
+    }
+    store_acts(l - 1);            // reads the operand tiles while the tensor core reads them too
+    tc::mbar_wait(bar_mma, ph);   // accumulators complete; operand and weight tiles are free
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();              // every thread is done reading the operand tiles (store_acts)
+    if (tid == 0 && l + 1 < a.n_layers) load_weights(l + 1);
+    {  // epilogue: TMEM (lane = row) -> bias, activation -> split -> operand tiles of the next layer
+      const int q = warp & 3, cq4 = warp >> 2;          // TMEM lane quarter; 32-column quarter of the accumulator
+      const int row = q * 32 + lane;
+      unsigned char* prow = A_hi + (row >> 3) * RG_BYTES + (row & 7) * 16;
+      const bool last = l == a.n_layers - 1;
+      const float* __restrict__ bias = Wc + a.b_off[l];   // padded layout: 16-byte aligned, length padded to 4
+#pragma unroll
+      for (int cc = 0; cc < 32; cc += 8) {
+        const int n = cq4 * 32 + cc;
+        if (n >= N) break;
+        uint32_t r[8], rc[8];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
+                     : "r"(taddr + 128u));
+        const bool two = n + 4 < N;   // widths are multiples of 4: the second float4 of the group is all in or all out
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        const float4 b1 = two ? __ldg(reinterpret_cast<const float4*>(bias + n + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + bb[j];
+          v[j] = last ? x : activate<ACT>(x);
+        }
+        float4 hi, lo;
+        tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+        *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = hi;
+        *reinterpret_cast<float4*>(prow + A_TILE + (n >> 2) * 128) = lo;
+        if (two) {
+          tc::split4(make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+          *reinterpret_cast<float4*>(prow + ((n >> 2) + 1) * 128) = hi;
+          *reinterpret_cast<float4*>(prow + A_TILE + ((n >> 2) + 1) * 128) = lo;
+        }
+      }
+      // a narrower layer leaves stale columns [N, K) of the previous one in the tiles: clear them (never taken at equal widths)
+      for (int ch = N / 4 + cq4; ch < (K + 3) / 4; ch += 4) {
+        *reinterpret_cast<float4*>(prow + ch * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(prow + A_TILE + ch * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  store_acts(a.n_layers - 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+}
+
+}  // namespace fused
+}  // namespace vihmc
