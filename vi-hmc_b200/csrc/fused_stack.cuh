@@ -13,7 +13,8 @@
 //     conflict-free); the fp32 activations the backward pass needs are written to HBM by a coalesced pass over the
 //     operand tiles (h = hi + lo, ~1 ulp from the unsplit value) that runs while the tensor core works on the next layer.
 // Shared memory: 2 x 52 KB (activations) + 2 x 45.5 KB (weights) = 195 KB: one CTA per SM, 512 threads (the epilogue is a
-// chain of TMEM load -> tanh -> split -> store latencies; 16 warps hide what 8 could not: measured 3.2 ms -> see profiles).
+// chain of TMEM load -> tanh -> split -> store latencies; 16 warps with a compile-time activation hide what 8 warps with a
+// runtime one could not: 3.2 ms -> 1.5 ms for the 8 trunk layers of 64 chains, against 2.25 ms for the per-layer GEMMs).
 // Eligibility (host side): every width a multiple of 4 and <= 104, input width <= 8 (the first layer runs on the FP32 pipes).
 #pragma once
 #include "tc_gemm.cuh"
@@ -29,6 +30,10 @@ constexpr int A_TILE = (BM / 8) * RG_BYTES;       // 53,248 B
 constexpr int B_TILE = (NPAD / 8) * RG_BYTES;     // 46,592 B
 constexpr int F_SMEM = 2 * A_TILE + 2 * B_TILE + 128;
 constexpr int F_THREADS = 512;                     // 16 warps: four per TMEM lane quarter, 32 accumulator columns each
+#ifndef VIHMC_FUSED_DIRECT_STORE
+#define VIHMC_FUSED_DIRECT_STORE 0   // 1: the epilogue writes fp32 activations from registers (row per thread: measured 1.73 ms
+                                     // vs 1.49 ms); 0: coalesced pass over the operand tiles
+#endif
 constexpr int MAX_IN0 = 8;                        // widest first-layer input handled by the FP32 first layer
 constexpr uint32_t kIdescF = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -103,8 +108,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // operand tiles start as zeros: the K padding (columns >= the layer width) must stay zero for every layer
-  for (int i = tid; i < 2 * A_TILE / 16; i += F_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the K padding of the operand tiles (chunks >= the first layer's width) must be zero: later layers only ever write
+  // chunks below their own width and clear what a wider predecessor left
+  for (int i = tid; i < BM * KCH; i += F_THREADS) {
+    const int row = i % BM, ch = i / BM;
+    if (4 * ch >= a.dims[0]) {
+      const int off = (row >> 3) * RG_BYTES + ch * 128 + (row & 7) * 16;
+      *reinterpret_cast<float4*>(A_hi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(A_lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -130,16 +143,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
     for (int k = 0; k < MAX_IN0; ++k) f[k] = (k < a.in_dim && grow < a.R) ? __ldg(a.input + grow * a.in_dim + k) : 0.0f;
     for (int ch = cq; 4 * ch < n0w; ch += 4) {
       float v[4];
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(Wc + a.b_off[0] + 4 * ch));
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = 4 * ch + j;
+        const float4* wrow = reinterpret_cast<const float4*>(Wc + a.w0_off + (long long)n * a.ldw0);   // rows padded to 4 floats
+        float w[MAX_IN0];
+#pragma unroll
+        for (int k4 = 0; k4 < MAX_IN0 / 4; ++k4) {
+          const float4 t = 4 * k4 < a.ldw0 ? __ldg(wrow + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          w[4 * k4] = t.x; w[4 * k4 + 1] = t.y; w[4 * k4 + 2] = t.z; w[4 * k4 + 3] = t.w;
+        }
         float acc = 0.0f;
 #pragma unroll
         for (int k = 0; k < MAX_IN0; ++k)
-          if (k < a.in_dim) acc = fmaf(__ldg(Wc + a.w0_off + (long long)n * a.ldw0 + k), f[k], acc);
-        acc += __ldg(Wc + a.b_off[0] + n);
+          if (k < a.in_dim) acc = fmaf(w[k], f[k], acc);
+        acc += bb[j];
         v[j] = a.n_layers > 1 ? activate<ACT>(acc) : acc;
       }
+      if (VIHMC_FUSED_DIRECT_STORE && grow < a.R)
+        *reinterpret_cast<float4*>(a.acts[0] + (c * a.R + grow) * n0w + 4 * ch) = make_float4(v[0], v[1], v[2], v[3]);
       float4 hi, lo;
       tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
       const int off = rg * RG_BYTES + ch * 128 + r8 * 16;
@@ -158,7 +182,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
     if (grow >= a.R) return;
     float* __restrict__ out = a.acts[l] + (c * a.R + grow) * nw + 4 * cq;
     const unsigned char* ph = A_hi + rg * RG_BYTES + cq * 128 + r8 * 16;
-    for (int ch = cq; 4 * ch < nw; ch += 4) {
+    for (int ch = cq; 4 * ch < nw; ch += 4) {   // (unrolling this loop to batch the loads was measured: no gain)
       const float4 hi = *reinterpret_cast<const float4*>(ph);
       const float4 lo = *reinterpret_cast<const float4*>(ph + A_TILE);
       *reinterpret_cast<float4*>(out) = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
@@ -186,7 +210,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
       }
       tc::mma_commit(bar_mma);
     }
-    store_acts(l - 1);            // reads the operand tiles while the tensor core reads them too
+    if (!VIHMC_FUSED_DIRECT_STORE) store_acts(l - 1);   // reads the operand tiles while the tensor core reads them too
     tc::mbar_wait(bar_mma, ph);   // accumulators complete; operand and weight tiles are free
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();              // every thread is done reading the operand tiles (store_acts)
@@ -197,6 +221,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
       unsigned char* prow = A_hi + (row >> 3) * RG_BYTES + (row & 7) * 16;
       const bool last = l == a.n_layers - 1;
       const float* __restrict__ bias = Wc + a.b_off[l];   // padded layout: 16-byte aligned, length padded to 4
+      const long long grow = r0 + row;
+      float* __restrict__ orow = a.acts[l] + (c * a.R + grow) * N;
 #pragma unroll
       for (int cc = 0; cc < 32; cc += 8) {
         const int n = cq4 * 32 + cc;
@@ -220,6 +246,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
           const float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + bb[j];
           v[j] = last ? x : activate<ACT>(x);
         }
+        if (VIHMC_FUSED_DIRECT_STORE && grow < a.R) {
+          *reinterpret_cast<float4*>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+          if (two) *reinterpret_cast<float4*>(orow + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
         float4 hi, lo;
         tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
         *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = hi;
@@ -240,7 +270,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
   }
-  store_acts(a.n_layers - 1);
+  if (!VIHMC_FUSED_DIRECT_STORE) store_acts(a.n_layers - 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
