@@ -162,11 +162,12 @@ static bool tensor_cores_enabled() {
 }
 
 template <int EPI>
-static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scratch = nullptr, int force = -1) {
+static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scratch = nullptr, int force = -1,
+                       float* rowsum_part = nullptr, float* rowsum_out = nullptr, long long rowsum_bs = 0, int* rowsum_done = nullptr) {
   if (g.M < 1 || g.N < 1 || g.K < 1 || batch < 1) return fail(VIHMC_ERR_INVALID, "gemm: empty problem");
   if (batch > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch > 65535");
   const bool tc = force < 0 ? tensor_cores_enabled() && tc_gemm_eligible(g) : force == 1;
-  if (tc) return launch_tc_gemm<EPI>(g, batch, st, scratch);
+  if (tc) return launch_tc_gemm<EPI>(g, batch, st, scratch, rowsum_part, rowsum_out, rowsum_bs, rowsum_done);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
   sgemm_batched_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
   VIHMC_LAUNCH_OK("sgemm_batched_kernel");
@@ -573,8 +574,12 @@ static int stack_backward(const Stack& s, const float* input, long long R, const
     g.B = l == 0 ? input : acts[l - 1]; g.b_bs = l == 0 ? 0 : R * in; g.b_sk = in; g.b_sn = 1;
     g.C = dWf + s.w_off[l]; g.c_bs = D; g.ldc = s.ldw[l];
     g.M = out; g.N = in; g.K = (int)R;
-    if (int rc = launch_gemm<EPI_STORE>(g, Cb, st, scratch)) return rc;
-    if (s.has_bias[l])   // dz_other is free until the dX GEMM below writes it: it holds the slab partials
+    // bias gradient = column sums of dz = row sums of opA: the tensor-core GEMM reads them off its operand stream when
+    // it can (MN-major A); dz_other is free until the dX GEMM below writes it and holds the partials either way
+    int bias_done = 0;
+    if (int rc = launch_gemm<EPI_STORE>(g, Cb, st, scratch, -1, s.has_bias[l] ? dz_other : nullptr,
+                                        s.has_bias[l] ? dWf + s.b_off[l] : nullptr, D, &bias_done)) return rc;
+    if (s.has_bias[l] && !bias_done)
       if (int rc = launch_colsum(dz_cur, R * out, R, out, out, dz_other, dWf + s.b_off[l], D, Cb, st)) return rc;
     if (l > 0) {
       // dz_prev[r,i] = (sum_o dz[r,o] W[o,i]) * act'(a_{l-1}[r,i])

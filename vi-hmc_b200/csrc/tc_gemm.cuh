@@ -54,6 +54,9 @@ struct GemmArgs {
   // partial product to split_buf[(s*batch + b), M, N]; splits <= 1 means a plain GEMM
   int splits, kc, batch;
   float* split_buf;
+  // row sums of opA over this CTA's K range (EPI_STORE, A staged MN-major, N <= 128): rowsum_part[(s*batch + b), M].
+  // With opA = dZ^T these are the bias gradients sum_r dz[r, o], read off the operand stream the GEMM loads anyway.
+  float* rowsum_part;
 };
 
 namespace tc {
@@ -353,12 +356,18 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
   // resident CTAs, and a third CTA parked in tcgen05.alloc is what hides the launch latency of the next tile.)
   const int nk = (g.K + BK - 1) / BK;
   float4 ra[2], rb[2];
+  const bool want_rowsum = (EPI == EPI_STORE) && g.rowsum_part != nullptr;   // host guarantees a_mode == LOAD_MNVEC
+  float4 rs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
   la.fetch(0, ra);
   lb.fetch(0, rb);
   for (int kt = 0; kt < nk; ++kt) {
     const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
     if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
+    if (want_rowsum) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { rs[i].x += ra[i].x; rs[i].y += ra[i].y; rs[i].z += ra[i].z; rs[i].w += ra[i].w; }
+    }
     stash(st, st + TILE_BYTES, la, ra);
     stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rb);
     if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
@@ -389,6 +398,32 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
   }
   mbar_wait(&mbar[(nk - 1) % STAGES], (uint32_t)((nk - 1) / STAGES) & 1u);   // commits complete in order: everything is done
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (want_rowsum && blockIdx.x == 0) {
+    // A thread's float4 i holds rows 32*(atom&3) + 4*(lane>>2) .. +3 at k rows (atom>>2)*4 + (lane&3) of every k-tile
+    // (atom = 2*warp + i): sum over the 4 k rows by shuffle, over the 4 k atoms (= warp pairs) through shared memory.
+    // Fixed order throughout: reproducible.
+    float* red = reinterpret_cast<float*>(smem);   // [4 k atoms][128 rows]; the operand stages are dead
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float v[4] = {rs[i].x, rs[i].y, rs[i].z, rs[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
+      }
+      const int atom = warp * 2 + i;
+      if ((lane & 3) == 0)
+        *reinterpret_cast<float4*>(red + (atom >> 2) * BM + (atom & 3) * 32 + (lane >> 2) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    if (tid < BM && m0 + tid < g.M) {
+      const float t = (red[tid] + red[BM + tid]) + (red[2 * BM + tid] + red[3 * BM + tid]);
+      g.rowsum_part[((long long)ksplit * g.batch + b) * g.M + m0 + tid] = t;
+    }
+    __syncthreads();
+  }
 
   // ---------------- epilogue ----------------
   // phase 1: TMEM -> registers -> shared tile [128][TILE_LD] (thread = one accumulator row, 8 columns per ld).
@@ -530,6 +565,17 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// out[b*out_bs + m] = sum_s part[(s*batch + b), m]  (bias gradients from the row sums of the weight-gradient GEMM)
+__global__ void rowsum_finish_kernel(const float* __restrict__ part, int splits, int batch, int M, float* __restrict__ out,
+                                     long long out_bs) {
+  const int b = blockIdx.x;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float s = 0.0f;
+    for (int k = 0; k < splits; ++k) s += part[((long long)k * batch + b) * M + m];
+    out[(long long)b * out_bs + m] = s;
+  }
+}
+
 constexpr int kSplitKChunk = 1024;      // K slice per CTA once K exceeds kSplitKThreshold
 constexpr int kSplitKThreshold = 2048;
 
@@ -551,8 +597,12 @@ inline int operand_mode(const float* base, long long bs, long long s_r, long lon
   return tc::LOAD_SCALAR;
 }
 
+// rowsum_out (EPI_STORE, optional): receives sum_k opA[b][m, k] at rowsum_out[b*rowsum_bs + m]; rowsum_part is scratch of
+// ceil(K/1024) * batch * M floats.  Returns VIHMC_ERR_UNSUPPORTED-free: when the fused row sums cannot be used
+// (*rowsum_done stays 0) the caller computes them itself.
 template <int EPI>
-static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch = nullptr) {
+static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch = nullptr, float* rowsum_part = nullptr,
+                          float* rowsum_out = nullptr, long long rowsum_bs = 0, int* rowsum_done = nullptr) {
   const int a_mode = operand_mode(g.A, g.a_bs, g.a_sm, g.a_sk);
   const int b_mode = operand_mode(g.B, g.b_bs, g.b_sn, g.b_sk);
   auto k = tc::tc_gemm_kernel<EPI>;
@@ -572,6 +622,8 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     if ((long long)batch * g.splits > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch * splits > 65535");
   }
   const int tiles_n = (g.N + tc::BN - 1) / tc::BN, tiles_m = (g.M + tc::BM - 1) / tc::BM;
+  const bool fuse_rowsum = EPI == EPI_STORE && rowsum_part != nullptr && rowsum_out != nullptr && a_mode == tc::LOAD_MNVEC;
+  g.rowsum_part = fuse_rowsum ? rowsum_part : nullptr;
   dim3 grid(tiles_n, tiles_m, batch * g.splits);
   k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
   VIHMC_LAUNCH_OK("tc_gemm_kernel");
@@ -581,6 +633,11 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     if (blocks > 148 * 8) blocks = 148 * 8;
     splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(scratch, g.splits, batch, g.M, g.N, g.C, g.c_bs, g.ldc);
     VIHMC_LAUNCH_OK("splitk_reduce_kernel");
+  }
+  if (fuse_rowsum) {
+    rowsum_finish_kernel<<<batch, 128, 0, st>>>(rowsum_part, g.splits, batch, g.M, rowsum_out, rowsum_bs);
+    VIHMC_LAUNCH_OK("rowsum_finish_kernel");
+    if (rowsum_done != nullptr) *rowsum_done = 1;
   }
   return VIHMC_OK;
 }
