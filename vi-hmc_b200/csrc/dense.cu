@@ -397,7 +397,8 @@ struct DensePlan {
   long long head_tiles, loss_tiles;
   // per-chain float counts
   long long act_a_floats, act_b_floats, per_chain_floats, scratch_per_chain;
-  long long img_floats;      // pre-split weight images of the fused trunk forward (0 when the trunk is not eligible)
+  long long img_floats;      // pre-split weight images of the fused trunk kernels (0 when the trunk is not eligible)
+  long long dzall_floats;    // fused trunk backward: dz of every layer below the top one + bias-gradient partials
   long long shared_floats;  // trunk features
 };
 
@@ -439,6 +440,44 @@ static int stack_forward_fused(const Stack& s, const float* input, long long R, 
   if (act == VIHMC_ACT_TANH) { if (int rc = launch(fused::fused_forward_kernel<VIHMC_ACT_TANH>)) return rc; }
   else { if (int rc = launch(fused::fused_forward_kernel<VIHMC_ACT_RELU>)) return rc; }
   VIHMC_LAUNCH_OK("fused_forward_kernel");
+  return VIHMC_OK;
+}
+
+// backward of one stack with the data pass in ONE kernel (fused_stack.cuh): dzs[top] holds d/d(pre-activation of the last
+// layer) on entry, dzs[l < top] are written by the kernel; the weight / bias gradients follow as one GEMM per layer.
+static int stack_backward_fused(const Stack& s, const float* input, long long R, const float* Wf, float* dWf, long long Dp,
+                                float* const* acts, float* const* dzs, int act, int Cb, float* img, float* bias_part, float* scratch,
+                                cudaStream_t st) {
+  const int top = s.n_layers - 1;
+  fused::ImgTable t{};
+  t.n = s.n_layers - 1;
+  for (int l = 1; l < s.n_layers; ++l) t.L[l - 1] = fused::ImgLayer{s.w_off[l], s.in_of(l), s.dims[l], 1, s.ldw[l]};   // W_l^T
+  fused::weight_image_kernel<<<dim3(t.n, Cb), 256, 0, st>>>(Wf, Dp, t, img);
+  VIHMC_LAUNCH_OK("weight_image_kernel");
+  fused::FusedBwdArgs a{};
+  for (int l = 0; l < s.n_layers; ++l) { a.dims[l] = s.dims[l]; a.acts[l] = acts[l]; a.dz[l] = dzs[l]; }
+  a.n_layers = s.n_layers; a.img = img; a.R = R;
+  const dim3 grid((unsigned)((R + tc::BM - 1) / tc::BM), Cb);
+  auto launch = [&](auto kernel) -> int {
+    VIHMC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::F_SMEM));
+    kernel<<<grid, fused::F_THREADS, fused::F_SMEM, st>>>(a);
+    return VIHMC_OK;
+  };
+  if (act == VIHMC_ACT_TANH) { if (int rc = launch(fused::fused_backward_kernel<VIHMC_ACT_TANH>)) return rc; }
+  else { if (int rc = launch(fused::fused_backward_kernel<VIHMC_ACT_RELU>)) return rc; }
+  VIHMC_LAUNCH_OK("fused_backward_kernel");
+  for (int l = top; l >= 0; --l) {
+    const int in = s.in_of(l), out = s.dims[l];
+    GemmArgs g{};   // dW[o,i] = sum_r dz[r,o] * a_in[r,i]
+    g.A = dzs[l]; g.a_bs = R * out; g.a_sm = 1; g.a_sk = out;
+    g.B = l == 0 ? input : acts[l - 1]; g.b_bs = l == 0 ? 0 : R * in; g.b_sk = in; g.b_sn = 1;
+    g.C = dWf + s.w_off[l]; g.c_bs = Dp; g.ldc = s.ldw[l];
+    g.M = out; g.N = in; g.K = (int)R;
+    int bias_done = 0;
+    if (int rc = launch_gemm<EPI_STORE>(g, Cb, st, scratch, -1, bias_part, dWf + s.b_off[l], Dp, &bias_done)) return rc;
+    if (!bias_done)
+      if (int rc = launch_colsum(dzs[l], R * out, R, out, out, bias_part, dWf + s.b_off[l], Dp, Cb, st)) return rc;
+  }
   return VIHMC_OK;
 }
 
@@ -494,7 +533,12 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
   pl.img_floats = (pl.deeponet && fused_eligible(pl.b)) ? (long long)(pl.b.n_layers - 1) * (2 * fused::B_TILE / 4) + 64 : 0;
-  pl.per_chain_floats = pl.img_floats + pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
+  pl.dzall_floats = 0;
+  if (pl.img_floats > 0) {
+    const long long wb = pl.b.max_width();
+    pl.dzall_floats = (long long)(pl.b.n_layers - 1) * (pl.P * wb + 64) + ((pl.P + 127) / 128 + 16) * wb + 64;
+  }
+  pl.per_chain_floats = pl.dzall_floats + pl.img_floats + pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
   // shared by every chain: pad map, trunk features, padded copy of the targets
   pl.shared_floats = pl.D + 64 + (pl.deeponet ? pl.P * 5 + 64 + pl.N * pl.Pp + 64 : 0);
   return VIHMC_OK;
@@ -695,6 +739,14 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     float* prior_part = bb.take((long long)Cb * ((d + kFinSlab - 1) / kFinSlab));
     float* scratch = pl.scratch_per_chain > 0 ? bb.take((long long)Cb * pl.scratch_per_chain) : nullptr;
     float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
+    float* dzs_b[VIHMC_MAX_LAYERS] = {nullptr};
+    float* bias_part = nullptr;
+    if (pl.dzall_floats > 0 && grad != nullptr) {   // fused trunk backward keeps dz of every layer for the weight gradients
+      const long long wb = pl.b.max_width();
+      for (int l = 0; l < pl.b.n_layers - 1; ++l) dzs_b[l] = bb.take((long long)Cb * P * wb);
+      dzs_b[pl.b.n_layers - 1] = dz0;
+      bias_part = bb.take((long long)Cb * (((P + 127) / 128 + 16) * wb));
+    }
     const float* qb = q + c0 * d;
 
     if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st)) return rc;
@@ -739,7 +791,11 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
         t.B = Bout; t.b_bs = N * K; t.b_sk = K; t.b_sn = 1;
         t.C = dz0; t.c_bs = P * K; t.ldc = K; t.M = (int)P; t.N = K; t.K = (int)N;
         if (int rc = launch_gemm<EPI_STORE>(t, Cb, st)) return rc;
-        if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        if (bias_part != nullptr) {
+          if (int rc = stack_backward_fused(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dzs_b, p->act, Cb, img, bias_part, scratch, st)) return rc;
+        } else {
+          if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        }
       }
     } else {
       const float* O = acts_a[pl.a.n_layers - 1];

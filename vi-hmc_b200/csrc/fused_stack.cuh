@@ -276,5 +276,176 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward data pass of the same stack: dz_{l-1} = (dz_l W_l) * act'(a_{l-1}) for l = top .. 1, one kernel per row tile.
+// (autograd of my_make_func.py:53-61 / :69-77).  Same machinery as the forward kernel with the transposed weight images
+// (operand element (n = input unit, k = output unit) = W_l[k][n]); per layer:
+//   MMA (dz_l in the operand tiles x W_l^T image) -> TMEM; the epilogue stores the raw product as fp32 into the hi tile;
+//   a coalesced pass multiplies by act'(a_{l-1}) (activation tile prefetched from HBM into registers while the tensor core
+//   works), writes dz_{l-1} to HBM for the weight-gradient GEMM and splits it into the operand tiles of the next layer.
+// ---------------------------------------------------------------------------------------------------------------
+struct FusedBwdArgs {
+  int dims[VIHMC_MAX_LAYERS];
+  int n_layers;
+  const float* img;                        // transposed images of layers 1 .. n_layers-1: [Cb, n_layers-1, 2, B_TILE/4]
+  const float* acts[VIHMC_MAX_LAYERS];     // acts[l]: [Cb, R, dims[l]] (forward activations)
+  float* dz[VIHMC_MAX_LAYERS];             // dz[l]: [Cb, R, dims[l]]; dz[n_layers-1] is the input, the others are written
+  long long R;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(F_THREADS, 1) fused_backward_kernel(FusedBwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* A_hi = smem;
+  unsigned char* A_lo = smem + A_TILE;
+  unsigned char* B_hi = smem + 2 * A_TILE;
+  uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + 2 * A_TILE + 2 * B_TILE);
+  uint64_t* bar_mma = bar_b + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long c = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * BM;
+  const int n_img = a.n_layers - 1, top = a.n_layers - 1;
+
+  if (tid == 0) {
+    tc::mbar_init(bar_b, 1);
+    tc::mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  auto load_weights = [&](int l) {   // thread 0: image of layer l (images are stored in layer order 1 .. top)
+    const float* src = a.img + (c * n_img + (l - 1)) * (2 * B_TILE / 4);
+    const uint32_t bytes = 2u * B_TILE;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar_b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(B_hi)),
+                 "l"(src), "r"(bytes), "r"(tc::smem_u32(bar_b))
+                 : "memory");
+  };
+  if (tid == 0) load_weights(top);
+
+  // coalesced mapping of the passes: warp -> row group, lane -> (row r8 = lane%8, chunks lane/8 + 4i)
+  const int r8 = lane & 7, cq = lane >> 3, rg = warp;
+  const long long grow = r0 + rg * 8 + r8;
+  const bool rvalid = grow < a.R;
+  const int poff = rg * RG_BYTES + cq * 128 + r8 * 16;
+  constexpr int NCH = (KCH + 3) / 4;
+
+  {  // incoming gradient tile -> operand tiles (zero beyond its width and beyond the matrix)
+    const int nw = a.dims[top];
+    const float* __restrict__ src = a.dz[top] + (c * a.R + grow) * nw + 4 * cq;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = cq + 4 * i;
+      if (ch >= KCH) break;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rvalid && 4 * ch < nw) v = __ldg(reinterpret_cast<const float4*>(src + 16 * i));
+      float4 hi, lo;
+      tc::split4(v, hi, lo);
+      *reinterpret_cast<float4*>(A_hi + poff + i * 4 * 128) = hi;
+      *reinterpret_cast<float4*>(A_lo + poff + i * 4 * 128) = lo;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  uint32_t ph = 0;
+  for (int l = top; l >= 1; --l, ph ^= 1u) {
+    const int K = a.dims[l], N = a.dims[l - 1];
+    if (tid == 0) {
+      tc::mbar_wait(bar_b, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = tc::smem_u32(A_hi), sb = tc::smem_u32(B_hi);
+      const int ksteps = (K + 7) / 8;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t ko = (uint32_t)ks * 256u;
+        const uint64_t a_hi = tc::make_desc(sa + ko, 128, RG_BYTES), a_lo = tc::make_desc(sa + A_TILE + ko, 128, RG_BYTES);
+        const uint64_t b_hi = tc::make_desc(sb + ko, 128, RG_BYTES), b_lo = tc::make_desc(sb + B_TILE + ko, 128, RG_BYTES);
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        tc::mma_tf32(tmem_d, a_hi, b_hi, kIdescF, acc);
+        tc::mma_tf32(tmem_d + 128, a_lo, b_hi, kIdescF, acc);
+        tc::mma_tf32(tmem_d + 128, a_hi, b_lo, kIdescF, 1u);
+      }
+      tc::mma_commit(bar_mma);
+    }
+    // activation tile of layer l-1 into registers while the tensor core works
+    float4 h[NCH];
+    {
+      const float* __restrict__ hsrc = a.acts[l - 1] + (c * a.R + grow) * N + 4 * cq;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rvalid && 4 * (cq + 4 * i) < N) h[i] = __ldg(reinterpret_cast<const float4*>(hsrc + 16 * i));
+      }
+    }
+    tc::mbar_wait(bar_mma, ph);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && l - 1 >= 1) load_weights(l - 1);   // the weight tiles are free: fetch the next image
+    {  // epilogue: raw product (main + corrections) as fp32 into the hi tile, TMEM lane = row
+      const int q = warp & 3, cq4 = warp >> 2;
+      const int row = q * 32 + lane;
+      unsigned char* prow = A_hi + (row >> 3) * RG_BYTES + (row & 7) * 16;
+#pragma unroll
+      for (int cc = 0; cc < 32; cc += 8) {
+        const int n = cq4 * 32 + cc;
+        if (n >= N) break;
+        uint32_t r[8], rc[8];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
+                     : "r"(taddr + 128u));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+        *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = make_float4(v[0], v[1], v[2], v[3]);
+        if (n + 4 < N) *reinterpret_cast<float4*>(prow + ((n >> 2) + 1) * 128) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    {  // pass: dz_{l-1} = raw * act'(a_{l-1}); HBM copy for the weight-gradient GEMM; hi / lo operands of the next layer
+      float* __restrict__ out = a.dz[l - 1] + (c * a.R + grow) * N + 4 * cq;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int ch = cq + 4 * i;
+        if (ch >= KCH) break;
+        unsigned char* pa = A_hi + poff + i * 4 * 128;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // chunks in [N, K) held the previous layer's operand: cleared
+        if (4 * ch < N) {
+          const float4 raw = *reinterpret_cast<const float4*>(pa);
+          if (ACT == VIHMC_ACT_TANH) {
+            v.x = raw.x * (1.0f - h[i].x * h[i].x); v.y = raw.y * (1.0f - h[i].y * h[i].y);
+            v.z = raw.z * (1.0f - h[i].z * h[i].z); v.w = raw.w * (1.0f - h[i].w * h[i].w);
+          } else {
+            v.x = h[i].x > 0.0f ? raw.x : 0.0f; v.y = h[i].y > 0.0f ? raw.y : 0.0f;
+            v.z = h[i].z > 0.0f ? raw.z : 0.0f; v.w = h[i].w > 0.0f ? raw.w : 0.0f;
+          }
+          if (rvalid) *reinterpret_cast<float4*>(out + 16 * i) = v;
+        } else if (4 * ch >= K) {
+          continue;   // beyond both widths: already zero
+        }
+        float4 hi, lo;
+        tc::split4(v, hi, lo);
+        *reinterpret_cast<float4*>(pa) = hi;
+        *reinterpret_cast<float4*>(pa + A_TILE) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+}
+
 }  // namespace fused
 }  // namespace vihmc
