@@ -589,6 +589,16 @@ inline long long splitk_scratch_floats(int M, int N, int K, int batch) {
 // shapes the tensor-core kernel is used for; everything else stays on the FP32-SIMT kernel
 inline bool tc_gemm_eligible(const GemmArgs& g) { return g.M >= 32 && g.K >= 16 && (g.N >= 16 || g.K >= 512); }
 
+inline int tc_num_sms() {
+  static const int n = []() {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
 // staging mode of one operand: element (r, k) at base + b*bs + r*s_r + k*s_k
 inline int operand_mode(const float* base, long long bs, long long s_r, long long s_k) {
   const bool aligned = (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && bs % 4 == 0;
@@ -616,7 +626,19 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
   if (EPI == EPI_STORE && scratch != nullptr && g.K > kSplitKThreshold) {
     // long reductions (dW = dZ^T X over thousands of rows): bound the length of one TMEM accumulation chain
     // (its fp32 accumulate truncates) and sum the slices with round-to-nearest adds
-    g.kc = kSplitKChunk;
+    // Slice length between 1024 (what the scratch is sized for) and 2048 (the accuracy bound), chosen so that the CTAs
+    // fill whole rounds of the GPU: 2 CTAs per SM hold TMEM at a time, and e.g. 64 chains x 10 slices = 640 CTAs would
+    // run 3 rounds for 2.16 rounds of work where 9 slices of 1152 run 2.
+    const long long tiles = (long long)((g.N + tc::BN - 1) / tc::BN) * ((g.M + tc::BM - 1) / tc::BM) * batch;
+    const int max_splits = (g.K + kSplitKChunk - 1) / kSplitKChunk, min_splits = (g.K + kSplitKThreshold - 1) / kSplitKThreshold;
+    const long long slots = 2LL * tc_num_sms();
+    long long best_cost = -1;
+    for (int sp = max_splits; sp >= min_splits && sp >= 1; --sp) {
+      const int kc = ((g.K + sp - 1) / sp + tc::BK - 1) / tc::BK * tc::BK;
+      const long long rounds = (tiles * sp + slots - 1) / slots;
+      const long long cost = rounds * kc;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; g.kc = kc; }
+    }
     g.splits = (g.K + g.kc - 1) / g.kc;
     g.split_buf = scratch;
     if ((long long)batch * g.splits > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch * splits > 65535");
