@@ -213,6 +213,17 @@ VIHMC_API int vihmc_gather_vi(const int64_t* sens_ind, const float* grad_W, floa
                     void* stream);
 
 /*
+ * Sensitivity scores of the VI -> HMC split selector (Neural_network/VI/sensitivity.py:71-126, eval_std_dydw / eval_jac):
+ *   scores[i] = sigma[i]^2 * mean_n (d o(x_n; w) / d w_i)^2,   n over the prob->N validation inputs prob->x,
+ * for the small-MLP family (out_dim 1), evaluated at the full weight vector `weights` (the VI means): prob->d must equal
+ * prob->D and prob->frozen / sens_ind must be NULL; prob->y and the prior / likelihood fields are not used.  weights, sigma,
+ * scores: device [D].  Workspace: vihmc_mlp_sensitivity_workspace_bytes(prob).
+ */
+VIHMC_API size_t vihmc_mlp_sensitivity_workspace_bytes(const vihmc_problem* prob);
+VIHMC_API int vihmc_mlp_sensitivity(const vihmc_problem* prob, const float* weights, const float* sigma, float* scores,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * The dense path's batched-GEMM building block, exported so that every operand staging mode of the tensor-core
  * kernel can be parity-tested on its own (it replaces the torch.nn.functional.linear / einsum calls of
  * Operator_network/VI_HMC/my_make_func.py:53-79 and the matmuls autograd derives from them):

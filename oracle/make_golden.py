@@ -50,6 +50,30 @@ def bnn_data_file():
     print("wrote", out)
 
 
+SENS_CASES = [("tanh_10x10", [10, 10], "tanh", 300), ("relu_10x10", [10, 10], "relu", 77), ("sine_16x16", [16, 16], "sine", 50),
+              ("tanh_32", [32], "tanh", 31)]
+
+
+def bnn_sensitivity_cases():
+    """Reference eval_std_dydw (Neural_network/VI/sensitivity.py:71-126: jacrev of the functional model) on synthetic VI
+    means / standard deviations; stores the inputs and the reference's scores."""
+    m = ref_loader.load_script("Neural_network/VI", "sensitivity", "ref_bnn_sens")
+    out = {}
+    for name, widths, act, n_val in SENS_CASES:
+        torch.manual_seed(0)
+        model = m.get_model(widths, act, True)
+        D = sum(p.numel() for p in model.parameters())
+        g = torch.Generator().manual_seed(len(name))
+        mu = 0.5 * torch.randn(D, generator=g)
+        sg = 0.01 + 0.1 * torch.rand(D, generator=g)
+        x = (2 * torch.rand(n_val, 1, generator=g) - 1)
+        s = m.eval_std_dydw((x, None), model, mu, sg)
+        out[f"{name}/mu"], out[f"{name}/sigma"], out[f"{name}/x"], out[f"{name}/scores"] = mu.numpy(), sg.numpy(), x.numpy(), s
+    path = os.path.join(GOLDEN, "bnn_sensitivity.npz")
+    np.savez(path, **out)
+    print("wrote", path)
+
+
 def bnn_vi_hmc_cases():
     """Reference closure Neural_network/VI_HMC/main_VI_HMC.py:28-153 on the bundled data."""
     m = ref_loader.load_bnn_vi_hmc()
@@ -168,3 +192,4 @@ if __name__ == "__main__":
     bnn_data_file()
     bnn_vi_hmc_cases()
     deeponet_cases()
+    bnn_sensitivity_cases()

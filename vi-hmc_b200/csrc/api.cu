@@ -17,6 +17,9 @@ namespace vihmc {
 bool mlp_small_supported(const vihmc_problem* p);
 int mlp_small_logp_grad(const vihmc_problem*, long long C, const float* q, float* logp, float* grad, cudaStream_t);
 int mlp_small_predict(const vihmc_problem*, long long C, const float* q, float* out, cudaStream_t);
+size_t mlp_small_sensitivity_workspace(const vihmc_problem*);
+int mlp_small_sensitivity(const vihmc_problem*, const float* weights, const float* sigma, float* out, void* ws, size_t ws_bytes,
+                          cudaStream_t);
 int mlp_small_sample(const vihmc_problem*, const vihmc_sampler_cfg*, long long C, const float* q0, float* samples,
                      const vihmc_sampler_io*, cudaStream_t);
 bool dense_supported(const vihmc_problem* p);
@@ -516,6 +519,19 @@ int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t a_lbo, uin
   if (int rc = device_check()) return rc;
   return dense_umma_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, a_layout_type, b_layout_type, idesc_extra, out,
                           static_cast<cudaStream_t>(stream));
+}
+
+size_t vihmc_mlp_sensitivity_workspace_bytes(const vihmc_problem* prob) {
+  if (prob == nullptr) return 0;
+  return mlp_small_sensitivity_workspace(prob);
+}
+
+int vihmc_mlp_sensitivity(const vihmc_problem* prob, const float* weights, const float* sigma, float* scores, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (prob == nullptr) return fail(VIHMC_ERR_INVALID, "sensitivity: null problem");
+  if (!mlp_small_supported(prob)) return fail(VIHMC_ERR_UNSUPPORTED, "sensitivity: only the small-MLP family is implemented");
+  return mlp_small_sensitivity(prob, weights, sigma, scores, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -135,6 +135,48 @@ int mlp_small_predict(const vihmc_problem* prob, long long C, const float* q, fl
   return dispatch(W, kOpPredict, P, a, st);
 }
 
+// out[i] = sigma_i^2 * (sum_chunks partial[chunk, i]) / N
+static __global__ void sensitivity_finish_kernel(const float* __restrict__ partial, int chunks, long long d, long long N,
+                                          const float* __restrict__ sigma, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  float s = 0.0f;
+  for (int c = 0; c < chunks; ++c) s += partial[(long long)c * d + i];
+  const float sg = sigma[i];
+  out[i] = s / (float)N * (sg * sg);
+}
+
+// vihmc_mlp_sensitivity: prob->x = validation inputs [N, in], d == D (no VI split); workspace = chunks * D floats
+size_t mlp_small_sensitivity_workspace(const vihmc_problem* prob) {
+  if (!mlp_small_supported(prob)) return 0;
+  int maxw = 0;
+  for (int l = 0; l < prob->n_layers_a - 1; ++l) maxw = prob->dims_a[l] > maxw ? prob->dims_a[l] : maxw;
+  const int NC = (32 / pick_width(maxw)) * 8;
+  return (size_t)((prob->N + NC - 1) / NC) * (size_t)prob->D * sizeof(float);
+}
+
+int mlp_small_sensitivity(const vihmc_problem* prob, const float* weights, const float* sigma, float* out, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  if (prob->d != prob->D || prob->sens_ind != nullptr || prob->frozen != nullptr)
+    return fail(VIHMC_ERR_INVALID, "sensitivity: pass the full weight vector (d == D, no frozen / sens_ind)");
+  if (weights == nullptr || sigma == nullptr || out == nullptr) return fail(VIHMC_ERR_INVALID, "sensitivity: null pointer");
+  vihmc_problem p = *prob;
+  if (p.y == nullptr) p.y = p.x;   // targets are not used; the staging code reads one float per data point
+  SmallParams P{};
+  int W = 0;
+  SmallLaunch a{};
+  if (int rc = fill_params(&p, P, W, 1, false, a.fast)) return rc;
+  const size_t need = mlp_small_sensitivity_workspace(&p);
+  if (ws == nullptr || ws_bytes < need) return fail(VIHMC_ERR_WORKSPACE, "sensitivity: workspace too small, need %zu bytes", need);
+  const int chunks = (int)((P.N + P.lay.NC - 1) / P.lay.NC);
+  a.warps_per_chain = 1; a.chains_per_block = 1; a.blocks = chunks; a.smem = (size_t)P.lay.total * sizeof(float); a.C = 1;
+  a.q = weights; a.out = static_cast<float*>(ws);
+  if (int rc = dispatch(W, kOpSensitivity, P, a, st)) return rc;
+  sensitivity_finish_kernel<<<(unsigned)((P.d + 127) / 128), 128, 0, st>>>(a.out, chunks, P.d, P.N, sigma, out);
+  VIHMC_LAUNCH_OK("sensitivity_finish_kernel");
+  return VIHMC_OK;
+}
+
 int mlp_small_sample(const vihmc_problem* prob, const vihmc_sampler_cfg* cfg, long long C, const float* q0, float* samples,
                      const vihmc_sampler_io* io, cudaStream_t st) {
   SmallParams P{};

@@ -728,6 +728,46 @@ __global__ void __launch_bounds__(128) mlp_small_predict_kernel(SmallParams P, l
 }
 
 // ------------------------------------------------------------------------------------------------
+// kernel 1c: sensitivity scores of the VI -> HMC split selector (vihmc_mlp_sensitivity)
+// Neural_network/VI/sensitivity.py:71-126: S_i = sigma_i^2 * mean_n (d o(x_n) / d w_i)^2 at w = the VI means.
+// One CTA (one warp per NW) per chunk of data points: forward, backward with d loss / d o = 1, then phase B with the
+// SQUARED per-point products; partial[chunk, i] = sum over the chunk's points, summed in fixed order by the finish kernel.
+// ------------------------------------------------------------------------------------------------
+template <int W, int NW>
+__global__ void __launch_bounds__(128) mlp_small_sensitivity_kernel(SmallParams P, const float* __restrict__ w,
+                                                                    float* __restrict__ partial) {
+  extern __shared__ __align__(16) float sm[];
+  using Cf = Cfg<W, NW>;
+  const int ct = threadIdx.x, bar = 1;
+  const int chunk = blockIdx.x;
+  const SmallLayout& L = P.lay;
+  chain_init<W, NW>(sm, P, w, ct, bar);
+  if (chunk > 0) {
+    stage_chunk<W, NW>(sm, P, ct, chunk);
+    chain_sync<NW>(bar);
+  }
+  forward_chunk<W, NW>(sm, P, ct, bar);
+  float* act = sm + L.act_base;
+  if (ct < Cf::NC) act[L.dO + ct] = ((long long)chunk * Cf::NC + ct < P.N) ? 1.0f : 0.0f;   // d o / d o
+  chain_sync<NW>(bar);
+  backward_chunk<W, NW>(sm, P, ct, bar);
+  const int* meta = reinterpret_cast<const int*>(sm + L.meta);
+  for (int i = ct; i < (int)P.d; i += Cf::T) {
+    const int m = meta[i];
+    const float4* A = reinterpret_cast<const float4*>(act + (m >> 16));
+    const float4* B = reinterpret_cast<const float4*>(act + (m & 0xffff));
+    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < Cf::NC / 4; ++c) {
+      const float4 a = A[c], b = B[c];
+      const float t0 = a.x * b.x, t1 = a.y * b.y, t2 = a.z * b.z, t3 = a.w * b.w;
+      acc0 = fmaf(t0, t0, acc0); acc1 = fmaf(t1, t1, acc1); acc2 = fmaf(t2, t2, acc2); acc3 = fmaf(t3, t3, acc3);
+    }
+    partial[(long long)chunk * P.d + i] = (acc0 + acc1) + (acc2 + acc3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel 2: the whole HMC run for C chains in one launch (vihmc_mlp_sample)
 // ------------------------------------------------------------------------------------------------
 struct SampleArgs {
@@ -899,7 +939,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
 // ------------------------------------------------------------------------------------------------
 // launch helpers shared by the per-width translation units
 // ------------------------------------------------------------------------------------------------
-enum SmallOp { kOpLogpGrad = 0, kOpPredict = 1, kOpSample = 2 };
+enum SmallOp { kOpLogpGrad = 0, kOpPredict = 1, kOpSample = 2, kOpSensitivity = 3 };
 
 struct SmallLaunch {
   int warps_per_chain, chains_per_block, blocks;
@@ -927,6 +967,11 @@ static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& 
     if (int rc = set_smem(k, a.smem)) return rc;
     k<<<a.blocks, threads, a.smem, st>>>(P, a.C, a.q, a.logp, a.grad);
     VIHMC_LAUNCH_OK("mlp_small_logp_grad_kernel");
+  } else if (op == kOpSensitivity) {   // q = weights, out = partial sums [blocks, d]
+    auto k = mlp_small_sensitivity_kernel<W, NW>;
+    if (int rc = set_smem(k, a.smem)) return rc;
+    k<<<a.blocks, 32 * NW, a.smem, st>>>(P, a.q, a.out);
+    VIHMC_LAUNCH_OK("mlp_small_sensitivity_kernel");
   } else if (op == kOpPredict) {
     auto k = mlp_small_predict_kernel<W, NW>;
     if (int rc = set_smem(k, a.smem)) return rc;
