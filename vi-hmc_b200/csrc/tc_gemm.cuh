@@ -579,10 +579,13 @@ __global__ void rowsum_finish_kernel(const float* __restrict__ part, int splits,
 constexpr int kSplitKChunk = 1024;      // K slice per CTA once K exceeds kSplitKThreshold
 constexpr int kSplitKThreshold = 2048;
 
+constexpr int kFillSplitMinK = 512;     // medium reductions are split only to put more CTAs on the GPU (few chains)
+constexpr int kFillSplitMax = 8;
+
 // floats of scratch a split-K GEMM of this shape needs (0 if it will not be split)
 inline long long splitk_scratch_floats(int M, int N, int K, int batch) {
-  if (K <= kSplitKThreshold) return 0;
-  const int splits = (K + kSplitKChunk - 1) / kSplitKChunk;
+  if (K < kFillSplitMinK) return 0;
+  const int splits = K > kSplitKThreshold ? (K + kSplitKChunk - 1) / kSplitKChunk : kFillSplitMax;
   return (long long)splits * batch * M * N;
 }
 
@@ -642,6 +645,17 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     g.splits = (g.K + g.kc - 1) / g.kc;
     g.split_buf = scratch;
     if ((long long)batch * g.splits > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch * splits > 65535");
+  } else if (EPI == EPI_STORE && scratch != nullptr && g.K >= kFillSplitMinK) {
+    // medium reduction, few output tiles (the branch's weight gradients: 64 chains = 64 CTAs): split to fill the GPU
+    const long long tiles = (long long)((g.N + tc::BN - 1) / tc::BN) * ((g.M + tc::BM - 1) / tc::BM) * batch;
+    long long sp = 2LL * tc_num_sms() / tiles;
+    if (sp > kFillSplitMax) sp = kFillSplitMax;
+    if (sp > g.K / 128) sp = g.K / 128;
+    if (sp >= 2 && (long long)batch * sp <= 65535) {
+      g.kc = (int)(((g.K + sp - 1) / sp + tc::BK - 1) / tc::BK * tc::BK);
+      g.splits = (g.K + g.kc - 1) / g.kc;
+      g.split_buf = scratch;
+    }
   }
   const int tiles_n = (g.N + tc::BN - 1) / tc::BN, tiles_m = (g.M + tc::BM - 1) / tc::BM;
   const bool fuse_rowsum = EPI == EPI_STORE && rowsum_part != nullptr && rowsum_out != nullptr && a_mode == tc::LOAD_MNVEC;
