@@ -397,7 +397,8 @@ struct DensePlan {
   long long head_tiles, loss_tiles;
   // per-chain float counts
   long long act_a_floats, act_b_floats, per_chain_floats, scratch_per_chain;
-  long long img_floats;      // pre-split weight images of the fused trunk kernels (0 when the trunk is not eligible)
+  bool fuse_a, fuse_b;       // the branch / trunk stack runs through the fused kernels
+  long long img_floats;      // pre-split weight images of the fused kernels (0 when no stack is eligible)
   long long dzall_floats;    // fused trunk backward: dz of every layer below the top one + bias-gradient partials
   long long shared_floats;  // trunk features
 };
@@ -411,9 +412,9 @@ static bool fused_enabled() {
   return on && tensor_cores_enabled();
 }
 
-// shapes fused_forward_kernel takes: every width a multiple of 4 and <= 104, narrow input, bias everywhere
+// shapes the fused kernels take: every width a multiple of 4 and <= 104, input at most 104 wide, bias everywhere
 static bool fused_eligible(const Stack& s) {
-  if (!fused_enabled() || s.n_layers < 2 || s.in_dim > fused::MAX_IN0) return false;
+  if (!fused_enabled() || s.n_layers < 2 || s.in_dim > fused::KPAD) return false;
   for (int l = 0; l < s.n_layers; ++l)
     if (s.dims[l] % 4 != 0 || s.dims[l] > fused::KPAD || !s.has_bias[l]) return false;
   return true;
@@ -423,8 +424,9 @@ static bool fused_eligible(const Stack& s) {
 static int stack_forward_fused(const Stack& s, const float* input, long long R, const float* Wf, long long Dp, float* const* acts,
                                int act, int Cb, float* img, cudaStream_t st) {
   fused::ImgTable t{};
-  t.n = s.n_layers - 1;
-  for (int l = 1; l < s.n_layers; ++l) t.L[l - 1] = fused::ImgLayer{s.w_off[l], s.dims[l], s.in_of(l), s.ldw[l], 1};
+  const int l0 = s.in_dim > fused::MAX_IN0 ? 0 : 1;   // a wide input makes the first layer a tensor-core layer too
+  t.n = s.n_layers - l0;
+  for (int l = l0; l < s.n_layers; ++l) t.L[l - l0] = fused::ImgLayer{s.w_off[l], s.dims[l], s.in_of(l), s.ldw[l], 1};
   fused::weight_image_kernel<<<dim3(t.n, Cb), 256, 0, st>>>(Wf, Dp, t, img);
   VIHMC_LAUNCH_OK("weight_image_kernel");
   fused::FusedFwdArgs a{};
@@ -532,11 +534,19 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long f = splitk_scratch_floats((int)pl.N, pl.K, (int)pl.P, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
-  pl.img_floats = (pl.deeponet && fused_eligible(pl.b)) ? (long long)(pl.b.n_layers - 1) * (2 * fused::B_TILE / 4) + 64 : 0;
+  // fused kernels (DeepONet stacks): weight images (the two stacks use the buffer one after the other), dz of every layer
+  pl.fuse_a = pl.deeponet && fused_eligible(pl.a);
+  pl.fuse_b = pl.deeponet && fused_eligible(pl.b);
+  const int n_img = (pl.fuse_a ? pl.a.n_layers : 0) > (pl.fuse_b ? pl.b.n_layers : 0) ? pl.a.n_layers : (pl.fuse_b ? pl.b.n_layers : 0);
+  pl.img_floats = n_img > 0 ? (long long)n_img * (2 * fused::B_TILE / 4) + 64 : 0;
   pl.dzall_floats = 0;
-  if (pl.img_floats > 0) {
+  if (pl.fuse_b) {
     const long long wb = pl.b.max_width();
-    pl.dzall_floats = (long long)(pl.b.n_layers - 1) * (pl.P * wb + 64) + ((pl.P + 127) / 128 + 16) * wb + 64;
+    pl.dzall_floats += (long long)(pl.b.n_layers - 1) * (pl.P * wb + 64) + ((pl.P + 127) / 128 + 16) * wb + 64;
+  }
+  if (pl.fuse_a) {
+    const long long wa = pl.a.max_width();
+    pl.dzall_floats += (long long)(pl.a.n_layers - 1) * (pl.N * wa + 64) + ((pl.N + 127) / 128 + 16) * wa + 64;
   }
   pl.per_chain_floats = pl.dzall_floats + pl.img_floats + pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
   // shared by every chain: pad map, trunk features, padded copy of the targets
@@ -739,20 +749,32 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     float* prior_part = bb.take((long long)Cb * ((d + kFinSlab - 1) / kFinSlab));
     float* scratch = pl.scratch_per_chain > 0 ? bb.take((long long)Cb * pl.scratch_per_chain) : nullptr;
     float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
+    float* dzs_a[VIHMC_MAX_LAYERS] = {nullptr};
     float* dzs_b[VIHMC_MAX_LAYERS] = {nullptr};
-    float* bias_part = nullptr;
-    if (pl.dzall_floats > 0 && grad != nullptr) {   // fused trunk backward keeps dz of every layer for the weight gradients
+    float* bias_part_a = nullptr;
+    float* bias_part_b = nullptr;
+    if (pl.fuse_b && grad != nullptr) {   // the fused backward keeps dz of every layer for the weight gradients
       const long long wb = pl.b.max_width();
       for (int l = 0; l < pl.b.n_layers - 1; ++l) dzs_b[l] = bb.take((long long)Cb * P * wb);
       dzs_b[pl.b.n_layers - 1] = dz0;
-      bias_part = bb.take((long long)Cb * (((P + 127) / 128 + 16) * wb));
+      bias_part_b = bb.take((long long)Cb * (((P + 127) / 128 + 16) * wb));
+    }
+    if (pl.fuse_a && grad != nullptr) {
+      const long long wa = pl.a.max_width();
+      for (int l = 0; l < pl.a.n_layers - 1; ++l) dzs_a[l] = bb.take((long long)Cb * N * wa);
+      dzs_a[pl.a.n_layers - 1] = dz0;
+      bias_part_a = bb.take((long long)Cb * (((N + 127) / 128 + 16) * wa));
     }
     const float* qb = q + c0 * d;
 
     if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st)) return rc;
-    if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
+    if (pl.fuse_a) {
+      if (int rc = stack_forward_fused(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, img, st)) return rc;
+    } else {
+      if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
+    }
     if (pl.deeponet) {
-      if (img != nullptr) {
+      if (pl.fuse_b) {
         if (int rc = stack_forward_fused(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, Cb, img, st)) return rc;
       } else {
         if (int rc = stack_forward(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;
@@ -784,15 +806,19 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
         h.B = Tout; h.b_bs = P * K; h.b_sk = K; h.b_sn = 1;
         h.C = dz0; h.c_bs = N * K; h.ldc = K; h.M = (int)N; h.N = K; h.K = (int)P;
         if (int rc = launch_gemm<EPI_STORE>(h, Cb, st, scratch)) return rc;
-        if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        if (bias_part_a != nullptr) {
+          if (int rc = stack_backward_fused(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dzs_a, p->act, Cb, img, bias_part_a, scratch, st)) return rc;
+        } else {
+          if (int rc = stack_backward(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dz0, dz1, p->act, Cb, st, scratch)) return rc;
+        }
         // dTout[p,k] = sum_n G[n,p] Bout[n,k]
         GemmArgs t{};
         t.A = G; t.a_bs = N * Pp; t.a_sm = 1; t.a_sk = Pp;
         t.B = Bout; t.b_bs = N * K; t.b_sk = K; t.b_sn = 1;
         t.C = dz0; t.c_bs = P * K; t.ldc = K; t.M = (int)P; t.N = K; t.K = (int)N;
         if (int rc = launch_gemm<EPI_STORE>(t, Cb, st)) return rc;
-        if (bias_part != nullptr) {
-          if (int rc = stack_backward_fused(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dzs_b, p->act, Cb, img, bias_part, scratch, st)) return rc;
+        if (bias_part_b != nullptr) {
+          if (int rc = stack_backward_fused(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dzs_b, p->act, Cb, img, bias_part_b, scratch, st)) return rc;
         } else {
           if (int rc = stack_backward(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dz0, dz1, p->act, Cb, st, scratch)) return rc;
         }
@@ -874,8 +900,12 @@ int dense_predict(const vihmc_problem* p, long long C, const float* q, float* ou
     float* part = bb.take(2LL * Cb * pl.head_tiles);
     float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
     if (int rc = scatter_padded(p, pl, sb.pad_map, q + c0 * d, Wf, Cb, st)) return rc;
-    if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
-    if (img != nullptr) {
+    if (pl.fuse_a) {
+      if (int rc = stack_forward_fused(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, img, st)) return rc;
+    } else {
+      if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
+    }
+    if (pl.fuse_b) {
       if (int rc = stack_forward_fused(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, Cb, img, st)) return rc;
     } else {
       if (int rc = stack_forward(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, false, Cb, st)) return rc;

@@ -15,7 +15,8 @@
 // Shared memory: 2 x 52 KB (activations) + 2 x 45.5 KB (weights) = 195 KB: one CTA per SM, 512 threads (the epilogue is a
 // chain of TMEM load -> tanh -> split -> store latencies; 16 warps with a compile-time activation hide what 8 warps with a
 // runtime one could not: 3.2 ms -> 1.5 ms for the 8 trunk layers of 64 chains, against 2.25 ms for the per-layer GEMMs).
-// Eligibility (host side): every width a multiple of 4 and <= 104, input width <= 8 (the first layer runs on the FP32 pipes).
+// Eligibility (host side): every width a multiple of 4 and <= 104; an input of at most 8 features goes through an FP32 first
+// layer (trunk), a wider one (<= 104, the branch's 101 sensors) is staged as the first tensor-core operand.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -71,7 +72,7 @@ struct FusedFwdArgs {
   long long b_off[VIHMC_MAX_LAYERS];
   int dims[VIHMC_MAX_LAYERS];
   int n_layers;
-  const float* img;                       // images of layers 1 .. n_layers-1: [Cb, n_layers-1, 2, B_TILE/4]
+  const float* img;                       // images of layers l0 .. n_layers-1 (l0 = 0 for a wide input, else 1): [Cb, n, 2, B_TILE/4]
   float* acts[VIHMC_MAX_LAYERS];          // acts[l]: [Cb, R, dims[l]]
   long long R;
   int act;                                // activation between layers (none after the last)
@@ -97,7 +98,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
   const long long c = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * BM;
   const float* __restrict__ Wc = a.Wf + c * a.Dp;
-  const int n_img = a.n_layers - 1;
+  // first layer: FP32 pipes when the input is narrow (trunk: 5 features), a tensor-core layer like the others when it is
+  // wide (branch: 101 sensors) -- then the operand tiles start as the split input tile and images exist for every layer
+  const int l0 = a.in_dim > MAX_IN0 ? 0 : 1;
+  const int n_img = a.n_layers - l0;
 
   if (tid == 0) {
     tc::mbar_init(bar_b, 1);
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
   // chunks below their own width and clear what a wider predecessor left
   for (int i = tid; i < BM * KCH; i += F_THREADS) {
     const int row = i % BM, ch = i / BM;
-    if (4 * ch >= a.dims[0]) {
+    if (l0 == 1 && 4 * ch >= a.dims[0]) {
       const int off = (row >> 3) * RG_BYTES + ch * 128 + (row & 7) * 16;
       *reinterpret_cast<float4*>(A_hi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(A_lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -124,17 +128,32 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
   const uint32_t tmem_d = *tmem_slot;
 
   auto load_weights = [&](int l) {   // thread 0: one bulk copy of layer l's hi + lo images, completion on bar_b
-    const float* src = a.img + (c * n_img + (l - 1)) * (2 * B_TILE / 4);
+    const float* src = a.img + (c * n_img + (l - l0)) * (2 * B_TILE / 4);
     const uint32_t bytes = 2u * B_TILE;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar_b)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(B_hi)),
                  "l"(src), "r"(bytes), "r"(tc::smem_u32(bar_b))
                  : "memory");
   };
-  if (tid == 0 && a.n_layers > 1) load_weights(1);
+  if (tid == 0 && l0 < a.n_layers) load_weights(l0);
 
-  // ---- layer 0 on the FP32 pipes: warp -> row group, lane -> (row r8 = lane%8, chunks lane/8 + 4j) ----
-  {
+  if (l0 == 0) {
+    // ---- wide input: the input tile itself becomes the first operand (rows of in_dim floats, any alignment) ----
+    const int r8 = lane & 7, cq = lane >> 3, rg = warp;
+    const long long grow = r0 + rg * 8 + r8;
+    const float* __restrict__ src = a.input + grow * a.in_dim;
+    for (int ch = cq; ch < KCH; ch += 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (grow < a.R && 4 * ch + j < a.in_dim) ? __ldg(src + 4 * ch + j) : 0.0f;
+      float4 hi, lo;
+      tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+      const int off = rg * RG_BYTES + ch * 128 + r8 * 16;
+      *reinterpret_cast<float4*>(A_hi + off) = hi;
+      *reinterpret_cast<float4*>(A_lo + off) = lo;
+    }
+  } else {
+    // ---- layer 0 on the FP32 pipes: warp -> row group, lane -> (row r8 = lane%8, chunks lane/8 + 4j) ----
     const int r8 = lane & 7, cq = lane >> 3, rg = warp;
     const int n0w = a.dims[0];
     const long long grow = r0 + rg * 8 + r8;
@@ -191,9 +210,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
     }
   };
 
-  for (int l = 1; l < a.n_layers; ++l) {
-    const int K = a.dims[l - 1], N = a.dims[l];
-    const uint32_t ph = (uint32_t)(l - 1) & 1u;
+  for (int l = l0; l < a.n_layers; ++l) {
+    const int K = l == 0 ? a.in_dim : a.dims[l - 1], N = a.dims[l];
+    const uint32_t ph = (uint32_t)(l - l0) & 1u;
     if (tid == 0) {
       tc::mbar_wait(bar_b, ph);   // this layer's weight images have landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -210,7 +229,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
       }
       tc::mma_commit(bar_mma);
     }
-    if (!VIHMC_FUSED_DIRECT_STORE) store_acts(l - 1);   // reads the operand tiles while the tensor core reads them too
+    if (!VIHMC_FUSED_DIRECT_STORE && l >= 1) store_acts(l - 1);   // reads the operand tiles while the tensor core reads them too
     tc::mbar_wait(bar_mma, ph);   // accumulators complete; operand and weight tiles are free
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();              // every thread is done reading the operand tiles (store_acts)
