@@ -172,3 +172,27 @@ def test_philox_known_answer_vectors():
     assert u.dtype == np.float32 and (u > 0).all() and (u < 1).all()
     z = philox_ref.normals(1, 0, 64, 0, 101)
     assert z.shape == (64, 101) and abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05
+
+
+def test_artifact_files_have_the_reference_formats(tmp_path):
+    """means/stds via torch.save, indices and samples via np.save with the reference's names, dtypes and shapes
+    (main_VI_HMC.py:76-79, :381, :418; sensitivity.py:219-234); a single chain's list of draws is saved exactly as
+    `np.save(path, params_hmc)` saves hamiltorch's list."""
+    from vihmc import artifacts
+
+    D, d, S = 141, 40, 7
+    rs = np.random.RandomState(0)
+    mu, sg = torch.from_numpy(rs.randn(D).astype(np.float32)), torch.from_numpy(rs.rand(D).astype(np.float32))
+    ind = rs.choice(D, d, replace=False)
+    artifacts.save_vi_artifacts(str(tmp_path), "uid1", mu, sg, ind, importance=rs.rand(D).astype(np.float32))
+    m2, s2, i2 = artifacts.load_vi_artifacts(str(tmp_path), "uid1")
+    assert torch.equal(m2, mu) and torch.equal(s2, sg) and m2.dtype == torch.float32
+    assert i2.dtype == np.int64 and np.array_equal(i2, np.sort(ind))
+    draws = [torch.from_numpy(rs.randn(d).astype(np.float32)) for _ in range(S)]
+    (path,) = artifacts.save_hmc_params(str(tmp_path) + "/", "uid1", draws)
+    ref = tmp_path / "ref.npy"
+    np.save(ref, np.stack([t.numpy() for t in draws]))   # what np.save makes of the reference's list of 1-D tensors
+    assert open(path, "rb").read() == open(ref, "rb").read()
+    assert artifacts.load_hmc_params(path, burn=2).shape == (S - 2, d)
+    paths = artifacts.save_hmc_params(str(tmp_path), "uid2", torch.from_numpy(rs.randn(S, 3, d).astype(np.float32)))
+    assert len(paths) == 3 and np.load(paths[1]).shape == (S, d)
