@@ -28,6 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "vi-hmc_b200")):
         sys.path.insert(0, p)
 
 METRIC, UNIT = "chain-grad-evals/sec", "chain-grad-evals/s"
+_REAL_STDOUT_FD = None               # set when fd 1 is redirected (multi-GPU runs, see run_ours)
 CHAINS_PER_GPU = 1024
 D_SAMPLED, STEP_SIZE, L_STEPS, TAU_OUT = 40, 5e-4, 196, 0.0025
 FLOP_PER_GRAD_EVAL = 14_000          # 2*[3*N*sum(in*out) - N*in_1*out_1], N=20, 1-10-10-1
@@ -189,9 +190,12 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the contract is ONE line on stdout: NCCL_DEBUG=VERSION (set on some boxes) prints its banner there
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # the contract is ONE line on stdout, but NCCL writes its "NCCL version ..." banner to file descriptor 1 when the
+        # communicator is created: point fd 1 at stderr for the run and keep the real stdout for the JSON line
+        global _REAL_STDOUT_FD
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -325,7 +329,10 @@ def main():
     a = ap.parse_args()
     line = run_reference(a.steps, a.warmup, a.gpus) if a.impl == "reference" else run_ours(a.steps, a.warmup, a.gpus, a.skip_cpu_baseline)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        if _REAL_STDOUT_FD is not None:
+            os.write(_REAL_STDOUT_FD, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
