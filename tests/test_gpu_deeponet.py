@@ -275,3 +275,43 @@ def test_tensor_core_gemm_every_staging_mode_vs_fp64(a_layout, b_layout, shape):
         err = (got.double() - ref).abs().max().item()
         scale = (A.double().abs() @ B.double().abs()).max().item()   # sum_k |a||b|: the natural error scale of a dot product
         assert err <= 2e-6 * scale, (tc, err, scale)
+
+
+_NOFUSE_SCRIPT = r"""
+import sys
+sys.path[:0] = [{root!r}, {pkg!r}, {tests!r}]
+import numpy as np, torch
+import cases
+from vihmc import engine
+g = cases.load_golden("deeponet_logp_grad.npz")
+out = {{}}
+for name in ("small", "full"):
+    inp = cases.don_inputs(name)
+    logp, grad = engine.logp_grad(cases.don_spec(inp, "full"), torch.from_numpy(g[name + "/full/q"]))
+    out[name + "/logp"], out[name + "/grad"] = logp.cpu().numpy(), grad.cpu().numpy()
+np.savez({dst!r}, **out)
+"""
+
+
+def test_fused_stack_kernels_agree_with_the_per_layer_path(tmp_path):
+    """The fused forward / backward stack kernels (csrc/fused_stack.cuh) against the per-layer GEMM path (VIHMC_DENSE_NOFUSE=1,
+    a separate process because the switch is read once): both meet the reference golden vectors and each other at 1e-5."""
+    import os, subprocess, sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for nofuse in ("0", "1"):
+        dst = str(tmp_path / f"nofuse{nofuse}.npz")
+        script = _NOFUSE_SCRIPT.format(root=root, pkg=os.path.join(root, "vi-hmc_b200"), tests=os.path.join(root, "tests"), dst=dst)
+        out = subprocess.run([sys.executable, "-c", script], env=dict(os.environ, VIHMC_DENSE_NOFUSE=nofuse), capture_output=True,
+                             text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[nofuse] = np.load(dst)
+    g = cases.load_golden("deeponet_logp_grad.npz")
+    for name in ("small", "full"):
+        for nofuse in ("0", "1"):
+            np.testing.assert_allclose(res[nofuse][f"{name}/logp"], g[f"{name}/full/logp"], rtol=RTOL)
+            for i in range(res[nofuse][f"{name}/grad"].shape[0]):
+                _close(res[nofuse][f"{name}/grad"][i], g[f"{name}/full/grad"][i])
+        for i in range(res["0"][f"{name}/grad"].shape[0]):
+            _close(res["0"][f"{name}/grad"][i], res["1"][f"{name}/grad"][i])
