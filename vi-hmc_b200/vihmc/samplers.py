@@ -14,7 +14,9 @@ Reference call sites mirrored here (argument names and meaning kept):
                                                   main_HMC_splitting.py:79 and :209-210 (split)
 
 What changes at this boundary: ``log_prob_func`` is a :class:`vihmc.spec.LogProbSpec` (or a list of them
-for ``Integrator.SPLITTING``) instead of a Python closure.  New optional keywords: ``num_chains``
+for ``Integrator.SPLITTING``) -- either built by the factories below, or recovered from one of the reference's own
+closures by ``vihmc.closure.spec_from_closure`` (so the reference's drivers run unmodified through the ``hamiltorch``
+drop-in package) and checked once against that closure at ``params_init``.  New optional keywords: ``num_chains``
 (params_init may also be ``[C, d]``), ``seed``, ``chain_offset``, ``return_result``.  With one chain the
 return value is hamiltorch's list of ``num_samples - burn`` 1-D tensors (so ``np.save`` writes the same
 ``(S, d)`` array); with C chains it is a ``[S - burn, C, d]`` tensor.
@@ -26,7 +28,7 @@ from typing import List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import engine
+from . import closure, engine
 from .spec import DeepONetArch, LogProbSpec, MLPArch, sliced_prior_sigma
 
 
@@ -71,17 +73,24 @@ def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, 
            integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, debug=False, desired_accept_rate=0.8,
            store_on_GPU=True, pass_grad=None, verbose=False, *, num_chains: Optional[int] = None, seed: int = 0,
            chain_offset: int = 0, return_result: bool = False, inject_momenta=None, inject_uniforms=None,
-           hamiltorch_fallback_rule: bool = True):
+           hamiltorch_fallback_rule: bool = True, verify_closures: bool = True):
     """hamiltorch.samplers.sample on the CUDA engine (see module docstring)."""
     if sampler == Sampler.RMHMC:
         raise NotImplementedError("RMHMC is not used by the reference and is not on the accelerated path")
     if inv_mass is not None:
         raise NotImplementedError("only the identity mass matrix (the reference's setting) is implemented")
     specs = list(log_prob_func) if isinstance(log_prob_func, (list, tuple)) else [log_prob_func]
-    for s in specs:
-        if not isinstance(s, (LogProbSpec, engine.Prepared)):
-            raise TypeError("log_prob_func must be the LogProbSpec returned by vihmc's define_model_log_prob "
-                            "(a CUDA engine cannot call a Python closure per leapfrog step)")
+    closures = {}
+    for i, s in enumerate(specs):
+        if isinstance(s, (LogProbSpec, engine.Prepared)):
+            continue
+        if not callable(s):
+            raise TypeError("log_prob_func must be a LogProbSpec (vihmc's define_model_log_prob) or one of the reference's "
+                            "own log_prob_func closures")
+        # one of the reference's closures: read the captured data, prior, likelihood and VI split back out of it
+        # (vihmc/closure.py) -- a CUDA engine cannot call Python per leapfrog step, and does not need to
+        closures[i] = s
+        specs[i] = closure.spec_from_closure(s)
     if integrator in (Integrator.SPLITTING, Integrator.SPLITTING_RAND, Integrator.SPLITTING_KMID):
         if integrator != Integrator.SPLITTING:
             raise NotImplementedError("only Integrator.SPLITTING (the reference's choice) is implemented")
@@ -100,6 +109,13 @@ def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, 
     spec0 = specs[0].spec if isinstance(specs[0], engine.Prepared) else specs[0]
     single = isinstance(params_init, torch.Tensor) and params_init.dim() == 1 and num_chains in (None, 1)
     q0 = _initial_states(spec0, params_init, num_chains, seed)
+    if closures and verify_closures:
+        # set-up check, once per closure: the closure's own value and autograd gradient at the first chain's start point
+        # must match the engine's for the recovered specification (raises closure.ClosureError otherwise)
+        for i, fn in closures.items():
+            recovered = specs[i]
+            specs[i] = engine.prepare(recovered)
+            closure.verify_closure(fn, recovered, q0[0], prepared=specs[i])
     res = engine.run_sampler(specs, q0, num_samples, num_steps_per_sample, float(step_size), burn=burn, integrator=integ,
                              adapt_step_size=nuts, desired_accept_rate=desired_accept_rate, seed=seed,
                              chain_offset=chain_offset, hamiltorch_fallback_rule=hamiltorch_fallback_rule,
