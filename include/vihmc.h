@@ -224,6 +224,19 @@ VIHMC_API int vihmc_mlp_sensitivity(const vihmc_problem* prob, const float* weig
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same scores for a DeepONet (Operator_network/VI/sensitivity.py:61-126, eval_std_dydw / eval_jac over the functional
+ * model my_make_func.py:46-85):
+ *   scores[i] = sigma[i]^2 * mean_{n < N, p < P} (d out[n, p] / d w_i)^2
+ * over the prob->N validation functions prob->x [N, in_a] and the prob->P trunk points prob->x2 they share.  The Jacobian
+ * (N * P * D floats in the reference) is never formed: the sum over p (over n for trunk parameters) is folded into a K x K
+ * Gram matrix whose Cholesky rows seed K back-propagations per row (csrc/don_sensitivity.cu).  d == D, frozen / sens_ind
+ * NULL, tanh or relu, widths and output neurons <= 128; y, prior and likelihood fields are not used.
+ */
+VIHMC_API size_t vihmc_deeponet_sensitivity_workspace_bytes(const vihmc_problem* prob);
+VIHMC_API int vihmc_deeponet_sensitivity(const vihmc_problem* prob, const float* weights, const float* sigma, float* scores,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * The dense path's batched-GEMM building block, exported so that every operand staging mode of the tensor-core
  * kernel can be parity-tested on its own (it replaces the torch.nn.functional.linear / einsum calls of
  * Operator_network/VI_HMC/my_make_func.py:53-79 and the matmuls autograd derives from them):

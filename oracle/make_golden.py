@@ -74,6 +74,40 @@ def bnn_sensitivity_cases():
     print("wrote", path)
 
 
+DON_SENS_CASES = [
+    # name, layer_width, in_branch, depth_branch, depth_trunk, output_neurons, act, [(n functions, p trunk points) per batch]
+    ("tanh_small", 16, 12, 3, 4, 8, "tanh", [(6, 35)]),          # n < K: the branch Gram matrix is rank deficient
+    ("relu_small", 24, 10, 3, 3, 16, "relu", [(20, 12)]),        # p < K: the trunk Gram matrix is rank deficient
+    ("tanh_loader", 16, 12, 3, 4, 8, "tanh", [(1, 9), (1, 9), (1, 9)]),   # the reference's loader: batch size 1, own trunk subset
+    ("tanh_shipped", 100, 101, 9, 9, 100, "tanh", [(3, 7)]),     # the shipped 172 401-parameter architecture
+]
+
+
+def deeponet_sensitivity_cases():
+    """Reference eval_std_dydw (Operator_network/VI/sensitivity.py:61-126: jacrev of the functional DeepONet) on synthetic VI means /
+    standard deviations; stores the inputs and the reference's scores."""
+    m = ref_loader.load_script("Operator_network/VI", "sensitivity", "ref_don_sens")
+    cfg = m.cfg
+    out = {}
+    for name, width, in_branch, db, dt, K, act, batches in DON_SENS_CASES:
+        cfg.branch_depth, cfg.trunk_depth, cfg.activation, cfg.dataset = db, dt, act, "Burgers"
+        torch.manual_seed(0)
+        model = m.DeepONet(width, in_branch, 5, db, dt, K, act, impose_bc=True)
+        D = sum(p.numel() for p in model.parameters())
+        g = torch.Generator().manual_seed(len(name))
+        mu = torch.cat([p.detach().flatten() for p in model.parameters()]) + 0.05 * torch.randn(D, generator=g)
+        sg = 0.001 + 0.01 * torch.rand(D, generator=g)
+        data = [(0.3 * torch.randn(n, 1, in_branch, generator=g), torch.rand(1, p, 2, generator=g)) for n, p in batches]
+        s = m.eval_std_dydw(data, model, mu, sg)
+        out[f"{name}/mu"], out[f"{name}/sigma"], out[f"{name}/scores"] = mu.numpy(), sg.numpy(), np.asarray(s, np.float32)
+        for bi, (xb, xt) in enumerate(data):
+            out[f"{name}/xb{bi}"], out[f"{name}/xt{bi}"] = xb.numpy(), xt.numpy()
+        print(name, "D", D, "scores max", float(np.max(s)), "nonzero", int(np.count_nonzero(s)))
+    path = os.path.join(GOLDEN, "deeponet_sensitivity.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def bnn_vi_hmc_cases():
     """Reference closure Neural_network/VI_HMC/main_VI_HMC.py:28-153 on the bundled data."""
     m = ref_loader.load_bnn_vi_hmc()
@@ -193,3 +227,4 @@ if __name__ == "__main__":
     bnn_vi_hmc_cases()
     deeponet_cases()
     bnn_sensitivity_cases()
+    deeponet_sensitivity_cases()

@@ -29,7 +29,7 @@ import types
 
 REFERENCE_ROOT = os.environ.get("VIHMC_REFERENCE_ROOT", "/root/reference")
 
-_LOCAL_MODULES = ("config", "config_splitting", "config_sens", "util", "my_make_func", "model")
+_LOCAL_MODULES = ("config", "config_splitting", "config_sens", "util", "utils", "my_make_func", "model")
 
 
 def reference_available() -> bool:

@@ -22,6 +22,9 @@ int mlp_small_sensitivity(const vihmc_problem*, const float* weights, const floa
                           cudaStream_t);
 int mlp_small_sample(const vihmc_problem*, const vihmc_sampler_cfg*, long long C, const float* q0, float* samples,
                      const vihmc_sampler_io*, cudaStream_t);
+size_t deeponet_sensitivity_workspace(const vihmc_problem*);
+int deeponet_sensitivity(const vihmc_problem*, const float* weights, const float* sigma, float* scores, void* ws, size_t ws_bytes,
+                         cudaStream_t);
 bool dense_supported(const vihmc_problem* p);
 size_t dense_workspace_bytes(const vihmc_problem*, long long C);
 int dense_logp_grad(const vihmc_problem*, long long C, const float* q, float* logp, float* grad, void* ws, size_t ws_bytes,
@@ -532,6 +535,18 @@ int vihmc_mlp_sensitivity(const vihmc_problem* prob, const float* weights, const
   if (prob == nullptr) return fail(VIHMC_ERR_INVALID, "sensitivity: null problem");
   if (!mlp_small_supported(prob)) return fail(VIHMC_ERR_UNSUPPORTED, "sensitivity: only the small-MLP family is implemented");
   return mlp_small_sensitivity(prob, weights, sigma, scores, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t vihmc_deeponet_sensitivity_workspace_bytes(const vihmc_problem* prob) {
+  if (prob == nullptr) return 0;
+  return deeponet_sensitivity_workspace(prob);
+}
+
+int vihmc_deeponet_sensitivity(const vihmc_problem* prob, const float* weights, const float* sigma, float* scores, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (prob == nullptr) return fail(VIHMC_ERR_INVALID, "deeponet sensitivity: null problem");
+  return deeponet_sensitivity(prob, weights, sigma, scores, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -68,6 +68,8 @@ SYMBOLS = {
     "vihmc_sample_host": (C.c_int, [_PP, _I32, _PC, _I64, _V, _V, _PIO]),
     "vihmc_mlp_sensitivity_workspace_bytes": (_SZ, [_PP]),
     "vihmc_mlp_sensitivity": (C.c_int, [_PP, _V, _V, _V, _V, _SZ, _V]),
+    "vihmc_deeponet_sensitivity_workspace_bytes": (_SZ, [_PP]),
+    "vihmc_deeponet_sensitivity": (C.c_int, [_PP, _V, _V, _V, _V, _SZ, _V]),
     "vihmc_debug_umma": (C.c_int, [_V, _V] + [C.c_uint32] * 7 + [_V, _V]),
     "vihmc_gemm_batched": (C.c_int, [_V, _I64, _I64, _I64, _V, _I64, _I64, _I64, _V, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
 }
