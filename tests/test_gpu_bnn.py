@@ -340,3 +340,51 @@ def test_specialised_evaluation_is_bit_identical_to_the_generic_one():
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
     assert digests[0] == digests[1]
+
+
+@pytest.mark.parametrize("force_general", [False, True])
+def test_divergent_trajectories_are_rejected_and_the_chain_survives(force_general):
+    """A step size far beyond stability overflows the trajectory (non-finite log-posterior): hamiltorch raises LogProbError
+    inside the iteration and rejects (util.py:106-118); the engine rejects on a non-finite H1.  Every stored row stays the
+    finite initial state, in both the persistent kernel and the general sampler."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    q0 = torch.from_numpy(case["q"][:4])
+    res = engine.run_sampler([spec], q0, 6, 30, 1e3, burn=0, seed=3, force_general=force_general)
+    assert int(res.accepted.sum()) == 0
+    assert torch.isfinite(res.samples).all()
+    for n in range(res.samples.shape[0]):
+        assert torch.equal(res.samples[n], q0)
+    assert not torch.isfinite(res.hamiltonians[:, :, 1]).all()     # the proposals really did blow up
+    # and a sane step size afterwards still samples (no sticky error state on the device)
+    ok = engine.run_sampler([spec], q0, 4, 10, 5e-4, burn=0, seed=3, force_general=force_general)
+    assert int(ok.accepted.sum()) > 0 and torch.isfinite(ok.samples).all()
+
+
+@pytest.mark.parametrize("force_general", [False, True])
+def test_minimal_shapes_one_chain_one_coordinate_one_step(force_general):
+    """Edge of every loop: C = 1 chain, d = 1 sampled coordinate of D = 141, one leapfrog step, one and two samples."""
+    x, y, _, _ = cases.synth.bnn_data()
+    mu, sigma, _ = cases.synth.bnn_vi_artifacts(141, 40, seed=1)
+    for coord in (0, 77, 140):      # first weight, a hidden-layer weight, the output bias
+        ind = np.array([coord], dtype=np.int64)
+        arch = cases.MLPArch(in_dim=1, widths=(10, 10), out_dim=1, act="tanh", last_bias=True)
+        sig = cases.sliced_prior_sigma(1, arch.tensor_numels(), [1.0] * 6)
+        spec = cases.LogProbSpec(arch=arch, x=x, y=y, loss="NLL", tau_out=0.0025, prior_sigma=torch.from_numpy(sig.astype(np.float32)),
+                                 frozen=mu, sens_ind=ind, vi_sigma=sigma)
+        closure = oc.BnnLogProb(x=x, y=y, widths=(10, 10), act="tanh", loss="NLL", tau_out=0.0025, prior=("sliced", [1.0] * 6),
+                                frozen=mu, sens_ind=ind, dtype=torch.float64)
+        q0 = mu[ind].clone()[None]
+        lp, gr = engine.logp_grad(spec, q0)
+        lp_ref, g_ref = oc.value_and_grad(closure, q0[0].double())
+        assert float(lp[0]) == pytest.approx(float(lp_ref), rel=RTOL)
+        assert float(gr[0, 0]) == pytest.approx(float(g_ref[0]), rel=1e-4, abs=1e-4 * abs(float(g_ref[0])) + 1e-3)
+        for S in (1, 2):
+            p = torch.full((S, 1, 1), 0.3)
+            u = torch.full((S, 1), 1e-30)
+            res = engine.run_sampler([spec], q0, S, 1, 1e-5, burn=0, inject_momenta=p, inject_uniforms=u, force_general=force_general)
+            assert res.samples.shape == (S, 1, 1)
+            ref = hr.sample(closure, q0[0].double(), num_samples=S, num_steps_per_sample=1, step_size=1e-5, momenta=p[:, 0].double(),
+                            uniforms=u[:, 0])
+            np.testing.assert_allclose(res.samples[:, 0].numpy(), torch.stack(ref).numpy(), rtol=1e-5, atol=1e-6)

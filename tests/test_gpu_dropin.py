@@ -130,4 +130,4 @@ def test_sample_model_and_predict_model_entry_points_of_the_shim():
     oracle = cases.oc.BnnLogProb(x=xv, y=yv, widths=(10, 10), loss="regression", tau_out=400.0, prior=("tau", [1.0] * 6))
     for s, o, lp in zip(samples[2:], pred, logp):
         np.testing.assert_allclose(o.numpy(), oracle.forward(s).detach().numpy(), rtol=1e-5, atol=1e-5)
-        assert float(lp) == pytest.approx(float(oracle(s)), rel=1e-5)
+        assert float(lp) == pytest.approx(float(oracle(s).detach()), rel=1e-5)
