@@ -237,6 +237,46 @@ VIHMC_API int vihmc_deeponet_sensitivity(const vihmc_problem* prob, const float*
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Bayes-by-Backprop trainer -- the producer of the VI artefacts (means / stds) the VI-HMC path consumes.
+ * Replaces train_model / validate_model / the epoch loop of Neural_network/VI/main_regression_VI.py:75-170,:279-346 and
+ * Operator_network/VI/main_VI_deeponet.py:24-118,:130-203 (BBBLinear: W = mu + softplus(rho) * eps, ELBO = Gaussian NLL + beta KL,
+ * torch.optim.Adam, ReduceLROnPlateau on the validation loss, best-validation checkpoint).  One optimiser step =
+ *   vihmc_vi_draw   W[E, D] = mu + softplus(rho) * eps (Philox, or eps = inject_eps[step] for parity tests)
+ *   vihmc_logp_grad on a prior-free problem with C = E and q = the W buffer -> the grad / logp buffers   (the hot-path kernel)
+ *   vihmc_vi_step   ELBO gradient w.r.t. (mu, rho), Adam update in place, loss bookkeeping
+ * and one epoch ends with vihmc_vi_epoch_end (validation loss from valid_logp[b] = log-likelihood at W = mu on validation batch b,
+ * plateau scheduler, history row (train loss, validation loss, learning rate), snapshot of the best (mu, rho)).  Step count, learning
+ * rate and scheduler state live in the device workspace: no call synchronises, the sequence can be captured in a CUDA graph.
+ * kl_form 0 = the KL the reference actually evaluates (BBBLinear.kl_loss passes (prior, posterior) into calculate_kl(mu_q, sig_q,
+ * mu_p, sig_p), i.e. KL(prior || q)); 1 = KL(q || prior).
+ */
+typedef struct vihmc_vi_cfg {
+  int32_t num_ens;            /* E: Monte-Carlo draws per optimiser step (cfg.num_ens) */
+  int32_t patience;           /* ReduceLROnPlateau patience (cfg.lr_patience) */
+  int32_t kl_form;            /* see above */
+  int32_t reserved;
+  float lr_start;             /* cfg.lr_start */
+  float min_lr;               /* 1e-5 in the reference */
+  float lr_factor;            /* 0.1 (torch default) */
+  float plateau_threshold;    /* 1e-4, relative (torch default) */
+  float beta;                 /* KL weight (cfg.beta_type as a float) */
+  float prior_mu, prior_sigma;/* cfg.priors */
+  float adam_b1, adam_b2, adam_eps; /* 0.9, 0.999, 1e-8 */
+  uint64_t seed;              /* Philox key of the eps draws */
+} vihmc_vi_cfg;
+
+VIHMC_API size_t vihmc_vi_workspace_bytes(int64_t D, int32_t num_ens);
+/* Device pointers into the workspace: 0 = W[E,D], 1 = grad[E,D], 2 = logp[E], 3 = eps[E,D], 4 = best mu[D], 5 = best rho[D]. */
+VIHMC_API void* vihmc_vi_buffer(void* workspace, int64_t D, int32_t num_ens, int32_t which);
+VIHMC_API int vihmc_vi_init(const vihmc_vi_cfg* cfg, int64_t D, void* workspace, size_t workspace_bytes, void* stream);
+VIHMC_API int vihmc_vi_draw(const vihmc_vi_cfg* cfg, int64_t D, const float* mu, const float* rho, const float* inject_eps,
+                  void* workspace, size_t workspace_bytes, void* stream);
+VIHMC_API int vihmc_vi_step(const vihmc_vi_cfg* cfg, int64_t D, float nll_scale, float* mu, float* rho, void* workspace,
+                  size_t workspace_bytes, void* stream);
+VIHMC_API int vihmc_vi_epoch_end(const vihmc_vi_cfg* cfg, int64_t D, const float* valid_logp, int32_t n_valid, float valid_nll_scale,
+                       const float* mu, const float* rho, float* history, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * The dense path's batched-GEMM building block, exported so that every operand staging mode of the tensor-core
  * kernel can be parity-tested on its own (it replaces the torch.nn.functional.linear / einsum calls of
  * Operator_network/VI_HMC/my_make_func.py:53-79 and the matmuls autograd derives from them):

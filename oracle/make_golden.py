@@ -108,6 +108,57 @@ def deeponet_sensitivity_cases():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+VI_TRAIN_CASES = [("adam_6x3", 6, 3, 1e-2, 5000), ("plateau_8x2", 8, 2, 0.3, 0)]   # name, epochs, num_ens, lr_start, lr_patience
+
+
+def bnn_vi_training_cases():
+    """The reference's own Bayesian_Net / train_model / validate_model / Adam / ReduceLROnPlateau loop
+    (Neural_network/VI/main_regression_VI.py:75-170,:300-335) on the bundled data.  BBBLinear draws eps with
+    torch.empty(size).normal_(0, 1) from the global generator, layer by layer (W then bias), draw by draw: reseeding the generator
+    and replaying the same calls recovers the eps stream, which is stored next to the reference's results."""
+    m = ref_loader.load_script("Neural_network/VI", "main_regression_VI", "ref_bnn_vi_train")
+    cfg = m.cfg
+    x_tr, y_tr, x_va, y_va = ref_loader.load_bnn_data()
+    out = {}
+    for name, epochs, num_ens, lr, patience in VI_TRAIN_CASES:
+        torch.manual_seed(len(name))
+        model = m.Bayesian_Net(cfg.priors, cfg.layer_width, cfg.input_size, cfg.output_size, cfg.activation, cfg.bias_on)
+        layers = [l for l in model.net if hasattr(l, "W_mu")]
+        flat = lambda attr_w, attr_b: torch.cat([torch.cat([getattr(l, attr_w).detach().flatten(), getattr(l, attr_b).detach().flatten()])
+                                                 for l in layers])
+        mu0, rho0 = flat("W_mu", "bias_mu").clone(), flat("W_rho", "bias_rho").clone()
+        opt = m.Adam(model.parameters(), lr=lr)
+        sched = m.lr_scheduler.ReduceLROnPlateau(opt, patience=patience, min_lr=1e-5)
+        loss = m.metrics.ELBO()
+        noise_param = torch.tensor(cfg.noise ** 2)
+        hist, eps_all = [], []
+        for ep in range(epochs):
+            torch.manual_seed(1000 + ep)
+            eps_ep = []
+            for j in range(num_ens):
+                eps_ep.append(torch.cat([torch.cat([torch.empty(l.W_mu.size()).normal_(0, 1).flatten(),
+                                                    torch.empty(l.bias_mu.size()).normal_(0, 1)]) for l in layers]))
+            eps_all.append(torch.stack(eps_ep))
+            torch.manual_seed(1000 + ep)
+            lr_used = opt.param_groups[0]["lr"]
+            tl = m.train_model((x_tr, y_tr), model, loss, opt, x_tr.shape[0], 1, num_ens, cfg.beta_type, epoch=ep, num_epochs=None,
+                               noise_param=noise_param)
+            vl = m.validate_model((x_va, y_va), model, loss, x_va.shape[0], cfg.beta_type, 1, epoch=ep, num_epochs=None,
+                                  noise_param=noise_param)
+            sched.step(vl)
+            hist.append([tl, vl, lr_used])
+        out[f"{name}/mu0"], out[f"{name}/rho0"] = mu0.numpy(), rho0.numpy()
+        out[f"{name}/eps"] = torch.stack(eps_all).numpy()
+        out[f"{name}/mu"], out[f"{name}/rho"] = flat("W_mu", "bias_mu").numpy(), flat("W_rho", "bias_rho").numpy()
+        out[f"{name}/history"] = np.asarray(hist, np.float64)
+        out[f"{name}/cfg"] = np.asarray([cfg.noise ** 2, cfg.priors["prior_mu"], cfg.priors["prior_sigma"], float(cfg.beta_type), lr, patience],
+                                        np.float64)
+        print(name, "history", np.asarray(hist)[[0, -1]])
+    path = os.path.join(GOLDEN, "bnn_vi_training.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def bnn_vi_hmc_cases():
     """Reference closure Neural_network/VI_HMC/main_VI_HMC.py:28-153 on the bundled data."""
     m = ref_loader.load_bnn_vi_hmc()
@@ -228,3 +279,4 @@ if __name__ == "__main__":
     deeponet_cases()
     bnn_sensitivity_cases()
     deeponet_sensitivity_cases()
+    bnn_vi_training_cases()

@@ -29,7 +29,9 @@ import types
 
 REFERENCE_ROOT = os.environ.get("VIHMC_REFERENCE_ROOT", "/root/reference")
 
-_LOCAL_MODULES = ("config", "config_splitting", "config_sens", "util", "utils", "my_make_func", "model")
+_LOCAL_MODULES = ("config", "config_splitting", "config_sens", "util", "utils", "my_make_func", "model", "metrics", "bayesian_model",
+                  "layers", "layers.BBB", "layers.BBB.BBBLinear", "layers.BBB.BBBConv", "layers.BBB_LRT", "layers.BBB_LRT.BBBLinear",
+                  "layers.BBB_LRT.BBBConv", "layers.misc")
 
 
 def reference_available() -> bool:

@@ -25,6 +25,14 @@ int mlp_small_sample(const vihmc_problem*, const vihmc_sampler_cfg*, long long C
 size_t deeponet_sensitivity_workspace(const vihmc_problem*);
 int deeponet_sensitivity(const vihmc_problem*, const float* weights, const float* sigma, float* scores, void* ws, size_t ws_bytes,
                          cudaStream_t);
+size_t vi_workspace_bytes(long long D, int E);
+void* vi_buffer(void* ws, long long D, int E, int which);
+int vi_init(const vihmc_vi_cfg*, long long D, void* ws, size_t ws_bytes, cudaStream_t);
+int vi_draw(const vihmc_vi_cfg*, long long D, const float* mu, const float* rho, const float* inject_eps, void* ws, size_t ws_bytes,
+            cudaStream_t);
+int vi_step(const vihmc_vi_cfg*, long long D, float nll_scale, float* mu, float* rho, void* ws, size_t ws_bytes, cudaStream_t);
+int vi_epoch_end(const vihmc_vi_cfg*, long long D, const float* valid_logp, int n_valid, float valid_nll_scale, const float* mu,
+                 const float* rho, float* history, void* ws, size_t ws_bytes, cudaStream_t);
 bool dense_supported(const vihmc_problem* p);
 size_t dense_workspace_bytes(const vihmc_problem*, long long C);
 int dense_logp_grad(const vihmc_problem*, long long C, const float* q, float* logp, float* grad, void* ws, size_t ws_bytes,
@@ -547,6 +555,34 @@ int vihmc_deeponet_sensitivity(const vihmc_problem* prob, const float* weights, 
   if (int rc = device_check()) return rc;
   if (prob == nullptr) return fail(VIHMC_ERR_INVALID, "deeponet sensitivity: null problem");
   return deeponet_sensitivity(prob, weights, sigma, scores, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t vihmc_vi_workspace_bytes(int64_t D, int32_t num_ens) { return vi_workspace_bytes(D, num_ens); }
+
+void* vihmc_vi_buffer(void* workspace, int64_t D, int32_t num_ens, int32_t which) {
+  if (workspace == nullptr || D < 1 || num_ens < 1) return nullptr;
+  return vi_buffer(workspace, D, num_ens, which);
+}
+
+int vihmc_vi_init(const vihmc_vi_cfg* cfg, int64_t D, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = device_check()) return rc;
+  return vi_init(cfg, D, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int vihmc_vi_draw(const vihmc_vi_cfg* cfg, int64_t D, const float* mu, const float* rho, const float* inject_eps, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  return vi_draw(cfg, D, mu, rho, inject_eps, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int vihmc_vi_step(const vihmc_vi_cfg* cfg, int64_t D, float nll_scale, float* mu, float* rho, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  return vi_step(cfg, D, nll_scale, mu, rho, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int vihmc_vi_epoch_end(const vihmc_vi_cfg* cfg, int64_t D, const float* valid_logp, int32_t n_valid, float valid_nll_scale,
+                       const float* mu, const float* rho, float* history, void* workspace, size_t workspace_bytes, void* stream) {
+  return vi_epoch_end(cfg, D, valid_logp, n_valid, valid_nll_scale, mu, rho, history, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

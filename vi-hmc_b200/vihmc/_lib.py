@@ -44,6 +44,15 @@ class SamplerIO(C.Structure):
     ]
 
 
+class ViCfg(C.Structure):
+    _fields_ = [
+        ("num_ens", C.c_int32), ("patience", C.c_int32), ("kl_form", C.c_int32), ("reserved", C.c_int32),
+        ("lr_start", C.c_float), ("min_lr", C.c_float), ("lr_factor", C.c_float), ("plateau_threshold", C.c_float),
+        ("beta", C.c_float), ("prior_mu", C.c_float), ("prior_sigma", C.c_float),
+        ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float), ("seed", C.c_uint64),
+    ]
+
+
 # every symbol include/vihmc.h declares: name -> (restype, argtypes)
 _PP, _PC, _PIO = C.POINTER(Problem), C.POINTER(SamplerCfg), C.POINTER(SamplerIO)
 _V, _I64, _U64, _F, _I32, _SZ = C.c_void_p, C.c_int64, C.c_uint64, C.c_float, C.c_int32, C.c_size_t
@@ -70,6 +79,12 @@ SYMBOLS = {
     "vihmc_mlp_sensitivity": (C.c_int, [_PP, _V, _V, _V, _V, _SZ, _V]),
     "vihmc_deeponet_sensitivity_workspace_bytes": (_SZ, [_PP]),
     "vihmc_deeponet_sensitivity": (C.c_int, [_PP, _V, _V, _V, _V, _SZ, _V]),
+    "vihmc_vi_workspace_bytes": (_SZ, [_I64, _I32]),
+    "vihmc_vi_buffer": (_V, [_V, _I64, _I32, _I32]),
+    "vihmc_vi_init": (C.c_int, [C.POINTER(ViCfg), _I64, _V, _SZ, _V]),
+    "vihmc_vi_draw": (C.c_int, [C.POINTER(ViCfg), _I64, _V, _V, _V, _V, _SZ, _V]),
+    "vihmc_vi_step": (C.c_int, [C.POINTER(ViCfg), _I64, _F, _V, _V, _V, _SZ, _V]),
+    "vihmc_vi_epoch_end": (C.c_int, [C.POINTER(ViCfg), _I64, _V, _I32, _F, _V, _V, _V, _V, _SZ, _V]),
     "vihmc_debug_umma": (C.c_int, [_V, _V] + [C.c_uint32] * 7 + [_V, _V]),
     "vihmc_gemm_batched": (C.c_int, [_V, _I64, _I64, _I64, _V, _I64, _I64, _I64, _V, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _V, _V]),
 }
