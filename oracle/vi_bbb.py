@@ -59,3 +59,44 @@ def train(x, y, x_val, y_val, widths, act, mu0, rho0, eps, noise_var, prior_mu, 
         if float(vloss) <= best:
             best, best_state = float(vloss), (mu.detach().clone(), rho.detach().clone())
     return mu.detach(), rho.detach(), best_state[0], best_state[1], np.asarray(hist, dtype=np.float64)
+
+
+def train_batches(batches, valid_batches, forward, mu0, rho0, eps, noise_var, prior_mu, prior_sigma, lr_start, lr_patience, train_size,
+                  valid_size, beta=1.0, min_lr=1e-5, dtype=torch.float32):
+    """The mini-batch form of the loop, Operator_network/VI/main_VI_deeponet.py:56-80 (train) and :105-118 (validate) with
+    metrics.py:29-31: loss = gaussian_nll_loss(mean) * train_size + beta * kl per batch, one Adam step per batch, epoch losses =
+    means over the batches.  batches: list of (inputs, y); forward(w, inputs) -> prediction shaped like y.  eps [epochs * n_batches,
+    num_ens, D].  (No reference-generated golden vector: the step arithmetic is pinned by the BNN trainer's.)"""
+    mu = mu0.to(dtype).clone().requires_grad_()
+    rho = rho0.to(dtype).clone().requires_grad_()
+    opt = torch.optim.Adam([mu, rho], lr=lr_start)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, patience=lr_patience, min_lr=min_lr)
+    nb = len(batches)
+    hist = []
+    for ep in range(eps.shape[0] // nb):
+        lr_used = opt.param_groups[0]["lr"]
+        tl = 0.0
+        for b, (inp, y) in enumerate(batches):
+            opt.zero_grad()
+            loss = 0.0
+            for j in range(eps.shape[1]):
+                sigma = torch.log1p(torch.exp(rho))
+                w = mu + eps[ep * nb + b, j].to(dtype) * sigma
+                pred = forward(w, inp)
+                loss = loss + F.gaussian_nll_loss(pred, y.to(dtype), noise_var * torch.ones_like(pred), reduction="mean") * train_size \
+                    + beta * kl_reference(mu, sigma, prior_mu, prior_sigma)
+            loss = loss / eps.shape[1]
+            loss.backward()
+            opt.step()
+            tl += float(loss.detach())
+        vl = 0.0
+        with torch.no_grad():
+            sigma = torch.log1p(torch.exp(rho))
+            for inp, y in valid_batches:
+                pred = forward(mu, inp)
+                vl += float(F.gaussian_nll_loss(pred, y.to(dtype), noise_var * torch.ones_like(pred), reduction="mean") * valid_size
+                            + beta * kl_reference(mu, sigma, prior_mu, prior_sigma))
+        vl /= max(len(valid_batches), 1)
+        sched.step(vl)
+        hist.append([tl / nb, vl, lr_used])
+    return mu.detach(), rho.detach(), np.asarray(hist, dtype=np.float64)

@@ -95,3 +95,41 @@ def test_cuda_trainer_philox_run_learns_and_writes_reference_artifacts(tmp_path)
     assert mu.dtype == torch.float32 and mu.shape == (141,)
     c = vi.train_bbb(mk(x, y, 0.0025), mk(xv, yv, 0.0025), **{**kw, "seed": 4})
     assert not torch.equal(a.mu, c.mu)
+
+
+@pytest.mark.gpu
+def test_cuda_trainer_deeponet_minibatches_vs_restated_loop():
+    """The DeepONet form of the loop (Operator_network/VI/main_VI_deeponet.py:56-118): two mini-batches of functions on the shared
+    trunk grid, loss = NLL(mean) * train_size + beta KL, one Adam step per batch -- against the torch restatement on the same eps."""
+    from vihmc import vi
+
+    inp = cases.don_inputs("small")
+    arch = inp["arch"]
+    x1, x2, y = inp["x1"], inp["x2"], inp["y"]
+    n, P, D = x1.shape[0], x2.shape[0], arch.num_params
+    half = n // 2
+    noise_var, epochs, E = 1.0, 4, 2
+    mk = lambda a, b: cases.LogProbSpec(arch=arch, x=a, x2=x2, y=b, loss="NLL", tau_out=noise_var, prior_sigma_scalar=1.0)
+    tspecs = [mk(x1[:half], y[:half]), mk(x1[half:], y[half:])]
+    vspec = mk(x1, y)
+    train_size = valid_size = float(n * P)
+    g = torch.Generator().manual_seed(0)
+    mu0 = inp["theta"] + 0.01 * torch.randn(D, generator=g)
+    rho0 = -5.0 + 0.1 * torch.randn(D, generator=g)
+    eps = torch.randn(epochs * 2, E, D, generator=g)
+    pri = dict(prior_mu=0.0, prior_sigma=0.1)
+    res = vi.train_bbb(tspecs, vspec, priors=pri, lr_start=1e-3, lr_patience=500, epochs=epochs, num_ens=E, beta=1.0,
+                       nll_scale=[train_size / (half * P), train_size / ((n - half) * P)], valid_nll_scale=valid_size / (n * P),
+                       mu0=mu0, rho0=rho0, inject_eps=eps)
+    kw = cases._don_kwargs(arch, torch.float32)
+    slots = cases.oc.deeponet_layout(kw["width_branch"], kw["width_trunk"], kw["in_branch"], kw["in_trunk"], kw["depth_branch"],
+                                     kw["depth_trunk"], kw["output_neurons"])
+
+    def forward(w, xb):
+        return cases.oc.deeponet_forward(xb.unsqueeze(1), x2.unsqueeze(0), cases.oc.unflatten(slots, w), kw["depth_branch"],
+                                         kw["depth_trunk"], kw["act"], kw["impose_bc"]).squeeze(1)
+    mu, rho, hist = ovi.train_batches([(x1[:half], y[:half]), (x1[half:], y[half:])], [(x1, y)], forward, mu0, rho0, eps, noise_var,
+                                      0.0, 0.1, 1e-3, 500, train_size, valid_size)
+    np.testing.assert_allclose(res.history.numpy()[:, :2], hist[:, :2], rtol=2e-4)
+    np.testing.assert_allclose(res.mu.numpy(), mu.numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(res.rho.numpy(), rho.numpy(), rtol=1e-3, atol=2e-4)
