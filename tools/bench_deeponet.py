@@ -50,16 +50,17 @@ def main():
     prep = engine.prepare(spec)
     engine.logp_grad(prep, q)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.reps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.reps + 1)]
+    ev[0].record()
+    for r in range(a.reps):
         logp, grad = engine.logp_grad(prep, q)
-    e1.record()
+        ev[r + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.reps
+    per_rep = [ev[r].elapsed_time(ev[r + 1]) for r in range(a.reps)]
+    ms = ev[0].elapsed_time(ev[-1]) / a.reps
     fl = flops_per_eval(arch, a.n, P)
     print(json.dumps({"workload": f"deeponet logp_grad N={a.n} P={P} D={arch.num_params} d={spec.d} chains={a.chains}",
-                      "ms_per_eval_batch": ms, "chain_grad_evals_per_s": a.chains / (ms * 1e-3),
+                      "ms_per_eval_batch": ms, "ms_per_rep": [round(t, 2) for t in per_rep], "chain_grad_evals_per_s": a.chains / (ms * 1e-3),
                       "gflop_per_unit": fl / 1e9, "tflops_fp32_equiv": a.chains * fl / (ms * 1e-3) / 1e12,
                       "workspace_gb": prep.workspace(a.chains).numel() / 2**30, "logp0": float(logp[0])}))
 

@@ -100,6 +100,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       : "memory");
 }
 
+// the same MMA with the A operand read from tensor memory ([taddr]: lane = row m, one 32-bit column per k) instead of through a
+// shared-memory descriptor: A_hi / A_lo then never cross the shared-memory port, which is what bounds this kernel (DESIGN.md 3.2b')
+__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -130,11 +140,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Inf/NaN guard (FSETP + predicate), which finite network values do not need (a non-finite value stays non-finite
 // or becomes NaN, and the sampler rejects either).
 __device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+// The split in the staging loops: TWO packed instructions per element instead of five.  These kernels are bound by instruction
+// issue (with the loads removed a long-K product still takes 60 % of its time, with the MMAs removed 85 %: tools/bench_gemm_shapes.py
+// on the VIHMC_DBG_* builds), and the split was half of a thread's instructions per k-tile.
+//   hi: Veltkamp's splitter with 2^13 + 1 -- g = fl(8193 v), hi = fl(g + fl(v - g)) is v rounded to nearest at 11 significant bits,
+//       i.e. a tf32 value -- as three fma.rn.f32x2 (Blackwell's packed FP32 pipe: two IEEE results per instruction);
+//   lo: v - hi, exact in fp32, NOT rounded to tf32: the tensor core drops the 13 low mantissa bits of a tf32 operand, a truncation
+//       toward zero OF LO.  lo's sign is unrelated to v's, so unlike truncating hi (the coherent bias described above) this is a
+//       zero-mean error of at most 2^-22 |v| per operand, below the fp32 rounding of the products themselves.
+// Non-finite or |v| > 4e34 inputs give NaN (8193 v overflows), which the sampler rejects like any non-finite log-posterior.
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void split2(float a, float b, float& ha, float& hb, float& la, float& lb) {
+  const unsigned long long v = pk2(a, b), c = pk2(8193.0f, 8193.0f), one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
+  const unsigned long long g = fma2(v, c, 0ull);
+  const unsigned long long d = fma2(g, mone, v);
+  const unsigned long long h = fma2(d, one, g);
+  const unsigned long long l = fma2(h, mone, v);
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(ha), "=f"(hb) : "l"(h));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(la), "=f"(lb) : "l"(l));
+}
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = rna_tf32(v.x); lo.x = rna_tf32(v.x - hi.x);
-  hi.y = rna_tf32(v.y); lo.y = rna_tf32(v.y - hi.y);
-  hi.z = rna_tf32(v.z); lo.z = rna_tf32(v.z - hi.z);
-  hi.w = rna_tf32(v.w); lo.w = rna_tf32(v.w - hi.w);
+  split2(v.x, v.y, hi.x, hi.y, lo.x, lo.y);
+  split2(v.z, v.w, hi.z, hi.w, lo.z, lo.w);
 }
 
 enum LoadMode { LOAD_SCALAR = 0, LOAD_KVEC = 1, LOAD_MNVEC = 2 };
@@ -176,6 +212,33 @@ struct TileLoader {
       }
     }
   }
+  // MODE >= 0: the staging mode is a compile-time constant (TMEM-A kernels): no mode branches in the k loop, and k-tiles that lie
+  // entirely below K -- all but the last -- skip the per-element bound tests.  MODE = -1: runtime mode.
+  template <int MODE>
+  __device__ __forceinline__ void fetch_t(int kt, float4 (&v)[2]) const {
+    if (MODE >= 0 && (kt + 1) * BK <= K) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* q = p[i] + (long long)kt * step;
+        if (MODE == LOAD_MNVEC) {
+          if (nrow[i] == 4) x = __ldg(reinterpret_cast<const float4*>(q));
+          else if (nrow[i] > 0) {
+            x.x = __ldg(q);
+            if (nrow[i] > 1) x.y = __ldg(q + 1);
+            if (nrow[i] > 2) x.z = __ldg(q + 2);
+          }
+        } else if (MODE == LOAD_KVEC) {
+          if (nrow[i] > 0) x = __ldg(reinterpret_cast<const float4*>(q));
+        } else if (nrow[i] > 0) {
+          x.x = __ldg(q); x.y = __ldg(q + s_k); x.z = __ldg(q + 2 * s_k); x.w = __ldg(q + 3 * s_k);
+        }
+        v[i] = x;
+      }
+    } else {
+      fetch(kt, v);
+    }
+  }
   __device__ __forceinline__ void fetch(int kt, float4 (&v)[2]) const {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -204,6 +267,66 @@ struct TileLoader {
     }
   }
 };
+
+// TMEM-A mode: a thread owns one row m of the A tile (its TMEM lane) and the 8 k of one half of a 16-deep k-tile
+// (warps 0-3: k 0..7, warps 4-7: k 8..15).  MN-major A (m contiguous): 8 loads, each coalesced over the warp's 32 rows;
+// K-major A: two float4 of the thread's own row.
+constexpr int ATM_ACCN = 112;                 // accumulator columns / instruction N in TMEM-A mode (N <= 112)
+constexpr int ATM_ACOL = 2 * ATM_ACCN;        // A stage: hi in columns [224, 240), lo in [240, 256) of the 256 allocated
+struct RowLoader {
+  const float* p;
+  long long s_k;
+  int K, kh, ok, vec;
+  __device__ __forceinline__ void init(const float* base, long long s_m, long long sk, int M, int K_, int m0, int mode, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row = m0 + 32 * (warp & 3) + lane;
+    kh = (warp >> 2) * 8; s_k = sk; K = K_; ok = row < M; vec = mode == LOAD_KVEC;
+    p = base + (long long)row * s_m + (long long)kh * sk;
+  }
+  template <int MODE>
+  __device__ __forceinline__ void fetch(int kt, float (&v)[8]) const {
+    const int k0 = kt * BK + kh;
+    const float* q = p + (long long)kt * BK * s_k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (!ok) return;
+    if (k0 + 8 <= K) {   // every k-tile but the last: no per-element bound tests
+      if (MODE == LOAD_KVEC) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(q)), y = __ldg(reinterpret_cast<const float4*>(q + 4));
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+      } else {
+        // element j is j * s_k floats further: byte offsets fit 32 bits (leading dimensions are < 2^26 floats)
+        const char* qb = reinterpret_cast<const char*>(q);
+        const unsigned skb = (unsigned)s_k * 4u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const float*>(qb + (size_t)((unsigned)j * skb)));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (k0 + j < K) v[j] = __ldg(q + (long long)j * s_k);
+    }
+  }
+};
+
+// split the thread's 8 values and write them to its TMEM lane: hi at column col, lo 16 columns further
+__device__ __forceinline__ void stash_tmem(uint32_t taddr, const float (&v)[8]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    float h0, h1, l0, l1;
+    split2(v[j], v[j + 1], h0, h1, l0, l1);
+    hi[j] = __float_as_uint(h0); hi[j + 1] = __float_as_uint(h1);
+    lo[j] = __float_as_uint(l0); lo[j + 1] = __float_as_uint(l1);
+  }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(hi[0]), "r"(hi[1]),
+               "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
+               : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + 16u), "r"(lo[0]), "r"(lo[1]),
+               "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7])
+               : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void stash(unsigned char* hi_tile, unsigned char* lo_tile, const TileLoader& ld, const float4 (&v)[2]) {
 #pragma unroll
@@ -313,8 +436,13 @@ __device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, lon
   return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && bs % 4 == 0 && ld % 4 == 0 && (N % 4 == 0 || row_pad_ok);
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
+// ATM (EPI_STORE, N <= 112, one n-tile): the A operand lives in tensor memory (see RowLoader); accumulators are 112 columns wide and
+// the single A stage takes the remaining 32 of the 256 allocated columns, so two CTAs per SM still hold TMEM at a time.
+constexpr int ATM_PF = 3;   // k-tiles of register prefetch in TMEM-A mode (see the main loop)
+template <int EPI, bool ATM = false, int AM = -1, int BMD = -1>
+__global__ void __launch_bounds__(THREADS, ATM ? 2 : 3) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
+  if (AM >= 0) { a_mode = AM; b_mode = BMD; }   // compile-time staging modes (all TMEM-A kernels, and the K-major / K-major fast variant)
+  constexpr int ACCN = ATM ? ATM_ACCN : BN;
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // swizzled MN-major tiles need 1 KB-aligned bases
   unsigned char* smem = smem_raw;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SMEM_BYTES - 128);
@@ -348,9 +476,14 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
   const uint32_t tmem_d = *tmem_slot;
 
   TileLoader la, lb;
-  la.init(g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_mode, tid);
+  RowLoader lr;
+  if (ATM) lr.init(g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_mode, tid);
+  else la.init(g.A + (long long)b * g.a_bs, g.a_sm, g.a_sk, g.M, g.K, m0, a_mode, tid);
   lb.init(g.B + (long long)b * g.b_bs, g.b_sn, g.b_sk, g.N, g.K, n0, b_mode, tid);
-  const uint32_t idesc = kIdesc | (a_mode == LOAD_MNVEC ? 1u << 15 : 0u) | (b_mode == LOAD_MNVEC ? 1u << 16 : 0u);
+  const uint32_t idesc = ATM ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ACCN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+                                (b_mode == LOAD_MNVEC ? 1u << 16 : 0u))
+                             : (kIdesc | (a_mode == LOAD_MNVEC ? 1u << 15 : 0u) | (b_mode == LOAD_MNVEC ? 1u << 16 : 0u));
+  const uint32_t a_taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)ATM_ACOL + (uint32_t)((warp >> 2) * 8);
 
   // One k-tile of register prefetch.  (Two tiles ahead was measured slower: 120+ registers leave room for only two
   // resident CTAs, and a third CTA parked in tcgen05.alloc is what hides the launch latency of the next tile.)
@@ -358,21 +491,90 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
   float4 ra[2], rb[2];
   const bool want_rowsum = (EPI == EPI_STORE) && g.rowsum_part != nullptr;   // host guarantees a_mode == LOAD_MNVEC
   float4 rs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-  la.fetch(0, ra);
-  lb.fetch(0, rb);
-  for (int kt = 0; kt < nk; ++kt) {
+  float rsum = 0.0f;
+  // TMEM-A mode keeps ATM_PF k-tiles of global loads in flight per thread.  These long-K products are bound by bytes in flight
+  // (Little's law): with ONE 16 KB k-tile per CTA and two TMEM-holding CTAs per SM, 32 KB per SM against a loaded memory latency of
+  // ~2 500 clk is 13 B/clk per SM = 3.6 TB/s for the whole GPU -- exactly the ~1 275 clk per k-tile both operand paths measured.
+  // Dropping A from shared memory is what makes room for it: 72 registers -> ~110 still fits the two CTAs that can hold TMEM.
+  float rva[ATM_PF][8];
+  float4 rbb[ATM_PF][2];
+  if (ATM) {
+#pragma unroll
+    for (int i = 0; i < ATM_PF; ++i)
+      if (i < nk) { lr.template fetch<AM>(i, rva[i]); lb.template fetch_t<BMD>(i, rbb[i]); }
+  } else {
+    la.template fetch_t<AM>(0, ra);
+    lb.template fetch_t<BMD>(0, rb);
+  }
+  auto issue_mma = [&](int kt, unsigned char* st, int s) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t sa = smem_u32(st);
+    const int k_left = g.K - kt * BK;
+    const int steps = k_left > 8 ? 2 : 1;
+    for (int ks = 0; ks < steps; ++ks) {
+      const uint64_t b_hi = step_desc(sa + 2 * TILE_BYTES, b_mode, ks), b_lo = step_desc(sa + 3 * TILE_BYTES, b_mode, ks);
+      const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
+      const uint32_t ta = tmem_d + (uint32_t)ATM_ACOL + (uint32_t)ks * 8u;
+#ifdef VIHMC_DBG_NOMMA
+      if (kt == 0)
+#endif
+      {
+        mma_tf32_ta(tmem_d, ta, b_hi, idesc, acc);
+        mma_tf32_ta(tmem_d + ACCN, ta + 16u, b_hi, idesc, acc);
+        mma_tf32_ta(tmem_d + ACCN, ta, b_lo, idesc, 1u);
+      }
+    }
+    mma_commit(&mbar[s]);
+  };
+  if (ATM) {
+    for (int kt0 = 0; kt0 < nk; kt0 += ATM_PF) {
+#pragma unroll
+      for (int i = 0; i < ATM_PF; ++i) {
+        const int kt = kt0 + i;
+        if (kt < nk) {
+          const int s = kt % STAGES;
+          unsigned char* st = smem + s * STAGE_BYTES;
+          // one A stage in tensor memory: the MMAs of the previous k-tile must have read it (commits complete in order, so
+          // this also frees the shared-memory stage of k-tile kt - STAGES)
+#ifdef VIHMC_DBG_NOWAIT
+          if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);
+#else
+          if (kt >= 1) mbar_wait(&mbar[(kt - 1) % STAGES], (uint32_t)((kt - 1) / STAGES) & 1u);
+#endif
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (want_rowsum)
+            rsum += ((rva[i][0] + rva[i][1]) + (rva[i][2] + rva[i][3])) + ((rva[i][4] + rva[i][5]) + (rva[i][6] + rva[i][7]));
+          stash_tmem(a_taddr, rva[i]);
+          stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rbb[i]);
+#ifndef VIHMC_DBG_NOLOAD
+          if (kt + ATM_PF < nk) {
+            lr.template fetch<AM>(kt + ATM_PF, rva[i]);
+            lb.template fetch_t<BMD>(kt + ATM_PF, rbb[i]);
+          }
+#endif
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncthreads();
+          if (tid == 0) issue_mma(kt, st, s);
+        }
+      }
+    }
+  }
+  for (int kt = 0; !ATM && kt < nk; ++kt) {
     const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
-    if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
-    if (want_rowsum) {
+    {
+      if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
+      if (want_rowsum) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { rs[i].x += ra[i].x; rs[i].y += ra[i].y; rs[i].z += ra[i].z; rs[i].w += ra[i].w; }
-    }
-    stash(st, st + TILE_BYTES, la, ra);
-    stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rb);
-    if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
-      la.fetch(kt + 1, ra);
-      lb.fetch(kt + 1, rb);
+        for (int i = 0; i < 2; ++i) { rs[i].x += ra[i].x; rs[i].y += ra[i].y; rs[i].z += ra[i].z; rs[i].w += ra[i].w; }
+      }
+      stash(st, st + TILE_BYTES, la, ra);
+      stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rb);
+      if (kt + 1 < nk) {   // next tile's global loads are in flight while the tensor core works on this one
+        la.template fetch_t<AM>(kt + 1, ra);
+        lb.template fetch_t<BMD>(kt + 1, rb);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
@@ -399,7 +601,16 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
   mbar_wait(&mbar[(nk - 1) % STAGES], (uint32_t)((nk - 1) / STAGES) & 1u);   // commits complete in order: everything is done
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  if (want_rowsum && blockIdx.x == 0) {
+  if (ATM && want_rowsum && blockIdx.x == 0) {
+    // a thread summed its row over its half of every k-tile: add the two halves (fixed order)
+    float* red = reinterpret_cast<float*>(smem);
+    __syncthreads();
+    red[(warp >> 2) * BM + (warp & 3) * 32 + lane] = rsum;
+    __syncthreads();
+    if (tid < BM && m0 + tid < g.M) g.rowsum_part[((long long)ksplit * g.batch + b) * g.M + m0 + tid] = red[tid] + red[BM + tid];
+    __syncthreads();
+  }
+  if (!ATM && want_rowsum && blockIdx.x == 0) {
     // A thread's float4 i holds rows 32*(atom&3) + 4*(lane>>2) .. +3 at k rows (atom>>2)*4 + (lane&3) of every k-tile
     // (atom = 2*warp + i): sum over the 4 k rows by shuffle, over the 4 k atoms (= warp pairs) through shared memory.
     // Fixed order throughout: reproducible.
@@ -443,7 +654,7 @@ __global__ void __launch_bounds__(THREADS, 3) tc_gemm_kernel(GemmArgs g, int a_m
                    : "r"(taddr));
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                    : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
-                   : "r"(taddr + (uint32_t)BN));
+                   : "r"(taddr + (uint32_t)ACCN));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       float v[8];
 #pragma unroll
@@ -624,6 +835,10 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     VIHMC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     configured = true;
   }
+  // TMEM-A variant: plain-store products with one n-tile of at most 112 columns and a vector-staged B (the weight-gradient
+  // GEMMs and the two head-backward products).  VIHMC_TC_TMEMA=0 keeps the shared-memory A path.
+  static const bool atm_on = []() { const char* e = getenv("VIHMC_TC_TMEMA"); return e == nullptr || atoi(e) != 0; }();
+  const bool use_atm = EPI == EPI_STORE && atm_on && g.N <= tc::ATM_ACCN && b_mode != tc::LOAD_SCALAR;
   g.splits = 1;
   g.batch = batch;
   if (EPI == EPI_STORE && scratch != nullptr && g.K > kSplitKThreshold) {
@@ -658,10 +873,35 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     }
   }
   const int tiles_n = (g.N + tc::BN - 1) / tc::BN, tiles_m = (g.M + tc::BM - 1) / tc::BM;
-  const bool fuse_rowsum = EPI == EPI_STORE && rowsum_part != nullptr && rowsum_out != nullptr && a_mode == tc::LOAD_MNVEC;
+  const bool fuse_rowsum = EPI == EPI_STORE && rowsum_part != nullptr && rowsum_out != nullptr && (a_mode == tc::LOAD_MNVEC || use_atm);
   g.rowsum_part = fuse_rowsum ? rowsum_part : nullptr;
   dim3 grid(tiles_n, tiles_m, batch * g.splits);
-  k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+  if (EPI == EPI_STORE && use_atm) {
+    using KernelT = void (*)(GemmArgs, int, int);
+    static const KernelT table[3][2] = {
+        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_KVEC>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_MNVEC>},
+        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_KVEC>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_MNVEC>},
+        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_KVEC>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_MNVEC>}};
+    static bool configured_atm = false;
+    if (!configured_atm) {
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 2; ++j)
+          VIHMC_CUDA_OK(cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      configured_atm = true;
+    }
+    table[a_mode][b_mode - 1]<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+  } else if (a_mode == tc::LOAD_KVEC && b_mode == tc::LOAD_KVEC) {
+    // both operands K-contiguous and aligned (the head product, the wide-MLP layers): staging modes fixed at compile time
+    auto kk = tc::tc_gemm_kernel<EPI, false, tc::LOAD_KVEC, tc::LOAD_KVEC>;
+    static bool configured_kk = false;
+    if (!configured_kk) {
+      VIHMC_CUDA_OK(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      configured_kk = true;
+    }
+    kk<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+  } else {
+    k<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+  }
   VIHMC_LAUNCH_OK("tc_gemm_kernel");
   if (g.splits > 1) {
     const long long total = (long long)batch * g.M * g.N;
