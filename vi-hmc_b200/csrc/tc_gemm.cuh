@@ -440,7 +440,8 @@ __device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, lon
 // the single A stage takes the remaining 32 of the 256 allocated columns, so two CTAs per SM still hold TMEM at a time.
 constexpr int ATM_PF = 3;   // k-tiles of register prefetch in TMEM-A mode (see the main loop)
 template <int EPI, bool ATM = false, int AM = -1, int BMD = -1>
-__global__ void __launch_bounds__(THREADS, ATM ? 2 : 3) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
+__global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
+  constexpr bool RING = AM >= 0;   // compile-time staging modes + ATM_PF k-tiles of register prefetch (two CTAs per SM)
   if (AM >= 0) { a_mode = AM; b_mode = BMD; }   // compile-time staging modes (all TMEM-A kernels, and the K-major / K-major fast variant)
   constexpr int ACCN = ATM ? ATM_ACCN : BN;
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // swizzled MN-major tiles need 1 KB-aligned bases
@@ -497,11 +498,15 @@ __global__ void __launch_bounds__(THREADS, ATM ? 2 : 3) tc_gemm_kernel(GemmArgs 
   // ~2 500 clk is 13 B/clk per SM = 3.6 TB/s for the whole GPU -- exactly the ~1 275 clk per k-tile both operand paths measured.
   // Dropping A from shared memory is what makes room for it: 72 registers -> ~110 still fits the two CTAs that can hold TMEM.
   float rva[ATM_PF][8];
-  float4 rbb[ATM_PF][2];
-  if (ATM) {
+  float4 raa[ATM_PF][2], rbb[ATM_PF][2];
+  if (RING) {
 #pragma unroll
     for (int i = 0; i < ATM_PF; ++i)
-      if (i < nk) { lr.template fetch<AM>(i, rva[i]); lb.template fetch_t<BMD>(i, rbb[i]); }
+      if (i < nk) {
+        if (ATM) lr.template fetch<AM>(i, rva[i]);
+        else la.template fetch_t<AM>(i, raa[i]);
+        lb.template fetch_t<BMD>(i, rbb[i]);
+      }
   } else {
     la.template fetch_t<AM>(0, ra);
     lb.template fetch_t<BMD>(0, rb);
@@ -514,19 +519,21 @@ __global__ void __launch_bounds__(THREADS, ATM ? 2 : 3) tc_gemm_kernel(GemmArgs 
     for (int ks = 0; ks < steps; ++ks) {
       const uint64_t b_hi = step_desc(sa + 2 * TILE_BYTES, b_mode, ks), b_lo = step_desc(sa + 3 * TILE_BYTES, b_mode, ks);
       const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
-      const uint32_t ta = tmem_d + (uint32_t)ATM_ACOL + (uint32_t)ks * 8u;
-#ifdef VIHMC_DBG_NOMMA
-      if (kt == 0)
-#endif
-      {
+      if (ATM) {
+        const uint32_t ta = tmem_d + (uint32_t)ATM_ACOL + (uint32_t)ks * 8u;
         mma_tf32_ta(tmem_d, ta, b_hi, idesc, acc);
         mma_tf32_ta(tmem_d + ACCN, ta + 16u, b_hi, idesc, acc);
         mma_tf32_ta(tmem_d + ACCN, ta, b_lo, idesc, 1u);
+      } else {
+        const uint64_t a_hi = step_desc(sa, a_mode, ks), a_lo = step_desc(sa + TILE_BYTES, a_mode, ks);
+        mma_tf32(tmem_d, a_hi, b_hi, idesc, acc);
+        mma_tf32(tmem_d + ACCN, a_lo, b_hi, idesc, acc);
+        mma_tf32(tmem_d + ACCN, a_hi, b_lo, idesc, 1u);
       }
     }
     mma_commit(&mbar[s]);
   };
-  if (ATM) {
+  if (RING) {
     for (int kt0 = 0; kt0 < nk; kt0 += ATM_PF) {
 #pragma unroll
       for (int i = 0; i < ATM_PF; ++i) {
@@ -536,22 +543,29 @@ __global__ void __launch_bounds__(THREADS, ATM ? 2 : 3) tc_gemm_kernel(GemmArgs 
           unsigned char* st = smem + s * STAGE_BYTES;
           // one A stage in tensor memory: the MMAs of the previous k-tile must have read it (commits complete in order, so
           // this also frees the shared-memory stage of k-tile kt - STAGES)
-#ifdef VIHMC_DBG_NOWAIT
-          if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);
-#else
-          if (kt >= 1) mbar_wait(&mbar[(kt - 1) % STAGES], (uint32_t)((kt - 1) / STAGES) & 1u);
-#endif
+          if (ATM) {
+            if (kt >= 1) mbar_wait(&mbar[(kt - 1) % STAGES], (uint32_t)((kt - 1) / STAGES) & 1u);
+          } else {
+            if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // shared-memory A: only the stage must be free
+          }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (want_rowsum)
-            rsum += ((rva[i][0] + rva[i][1]) + (rva[i][2] + rva[i][3])) + ((rva[i][4] + rva[i][5]) + (rva[i][6] + rva[i][7]));
-          stash_tmem(a_taddr, rva[i]);
+          if (ATM) {
+            if (want_rowsum)
+              rsum += ((rva[i][0] + rva[i][1]) + (rva[i][2] + rva[i][3])) + ((rva[i][4] + rva[i][5]) + (rva[i][6] + rva[i][7]));
+            stash_tmem(a_taddr, rva[i]);
+          } else {
+            if (want_rowsum) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) { rs[j].x += raa[i][j].x; rs[j].y += raa[i][j].y; rs[j].z += raa[i][j].z; rs[j].w += raa[i][j].w; }
+            }
+            stash(st, st + TILE_BYTES, la, raa[i]);
+          }
           stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rbb[i]);
-#ifndef VIHMC_DBG_NOLOAD
           if (kt + ATM_PF < nk) {
-            lr.template fetch<AM>(kt + ATM_PF, rva[i]);
+            if (ATM) lr.template fetch<AM>(kt + ATM_PF, rva[i]);
+            else la.template fetch_t<AM>(kt + ATM_PF, raa[i]);
             lb.template fetch_t<BMD>(kt + ATM_PF, rbb[i]);
           }
-#endif
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncthreads();
@@ -560,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, ATM ? 2 : 3) tc_gemm_kernel(GemmArgs 
       }
     }
   }
-  for (int kt = 0; !ATM && kt < nk; ++kt) {
+  for (int kt = 0; !RING && kt < nk; ++kt) {
     const int s = kt % STAGES;
     unsigned char* st = smem + s * STAGE_BYTES;
     {
