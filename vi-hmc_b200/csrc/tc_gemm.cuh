@@ -309,9 +309,8 @@ struct RowLoader {
   }
 };
 
-// split the thread's 8 values and write them to its TMEM lane: hi at column col, lo 16 columns further
-__device__ __forceinline__ void stash_tmem(uint32_t taddr, const float (&v)[8]) {
-  uint32_t hi[8], lo[8];
+// split the thread's 8 values (registers only) ...
+__device__ __forceinline__ void split8(const float (&v)[8], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
     float h0, h1, l0, l1;
@@ -319,6 +318,9 @@ __device__ __forceinline__ void stash_tmem(uint32_t taddr, const float (&v)[8]) 
     hi[j] = __float_as_uint(h0); hi[j + 1] = __float_as_uint(h1);
     lo[j] = __float_as_uint(l0); lo[j + 1] = __float_as_uint(l1);
   }
+}
+// ... and write them to its TMEM lane: hi at column col, lo 16 columns further
+__device__ __forceinline__ void store_tmem(uint32_t taddr, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(hi[0]), "r"(hi[1]),
                "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7])
                : "memory");
@@ -544,27 +546,34 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
           // one A stage in tensor memory: the MMAs of the previous k-tile must have read it (commits complete in order, so
           // this also frees the shared-memory stage of k-tile kt - STAGES)
           if (ATM) {
-            if (kt >= 1) mbar_wait(&mbar[(kt - 1) % STAGES], (uint32_t)((kt - 1) / STAGES) & 1u);
-          } else {
-            if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // shared-memory A: only the stage must be free
-          }
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (ATM) {
+            // Everything that does not touch the single A stage runs BEFORE the wait for the previous k-tile's MMAs, i.e. while the
+            // tensor core is still working on them: the split (registers), the B tile (its shared-memory stage was last read by
+            // k-tile kt - STAGES, complete since the wait of the previous iteration) and the next global loads.
+            uint32_t hi[8], lo[8];
             if (want_rowsum)
               rsum += ((rva[i][0] + rva[i][1]) + (rva[i][2] + rva[i][3])) + ((rva[i][4] + rva[i][5]) + (rva[i][6] + rva[i][7]));
-            stash_tmem(a_taddr, rva[i]);
+            split8(rva[i], hi, lo);
+            stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rbb[i]);
+            if (kt + ATM_PF < nk) {
+              lr.template fetch<AM>(kt + ATM_PF, rva[i]);
+              lb.template fetch_t<BMD>(kt + ATM_PF, rbb[i]);
+            }
+            if (kt >= 1) mbar_wait(&mbar[(kt - 1) % STAGES], (uint32_t)((kt - 1) / STAGES) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            store_tmem(a_taddr, hi, lo);
           } else {
+            if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // shared-memory A: only the stage must be free
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (want_rowsum) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) { rs[j].x += raa[i][j].x; rs[j].y += raa[i][j].y; rs[j].z += raa[i][j].z; rs[j].w += raa[i][j].w; }
             }
             stash(st, st + TILE_BYTES, la, raa[i]);
-          }
-          stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rbb[i]);
-          if (kt + ATM_PF < nk) {
-            if (ATM) lr.template fetch<AM>(kt + ATM_PF, rva[i]);
-            else la.template fetch_t<AM>(kt + ATM_PF, raa[i]);
-            lb.template fetch_t<BMD>(kt + ATM_PF, rbb[i]);
+            stash(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lb, rbb[i]);
+            if (kt + ATM_PF < nk) {
+              la.template fetch_t<AM>(kt + ATM_PF, raa[i]);
+              lb.template fetch_t<BMD>(kt + ATM_PF, rbb[i]);
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
