@@ -67,39 +67,58 @@ def initial_states(mu, sigma, ind, chains, chain0):
 # clocks sampling during the timed region (NVML; falls back to nvidia-smi)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """NVML is initialised and the first sample taken synchronously in __enter__ (nvmlInit can take longer than the whole
+    timed region on a fresh box); the thread then samples every 2 ms until __exit__, which takes a last sample itself."""
+
+    _NAMES = None
+
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.stop = index, [], set(), threading.Event()
         self.max_mhz = None
+        self.nv = self.h = None
         self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, nm in self._names.items():
+            if mask & bit:
+                self.reasons.add(nm)
 
     def _run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
             while not self.stop.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if mask & bit:
-                        self.reasons.add(nm)
+                self._sample()
                 time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"clock_sampling_failed:{type(e).__name__}")
 
     def __enter__(self):
-        self.thread.start()
-        time.sleep(0.01)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self._names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                           nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                           nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                           nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            self._sample()
+            self.thread.start()
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"clock_sampling_failed:{type(e).__name__}")
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.thread.join(timeout=2)
+        if self.thread.is_alive():
+            self.thread.join(timeout=2)
+        try:
+            if self.nv is not None:
+                self._sample()
+        except Exception:  # pragma: no cover
+            pass
 
     def summary(self):
         s = sorted(self.samples)
