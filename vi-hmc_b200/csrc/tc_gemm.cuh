@@ -396,23 +396,37 @@ __device__ __forceinline__ void epilogue_rows(const EpiCtx& e, float& ll_acc, fl
       if (nv > 2) bv.z = __ldg(e.biasb + e.n0 + c + 2);
       if (nv > 3) bv.w = __ldg(e.biasb + e.n0 + c + 3);
     }
-#pragma unroll 2
-    for (int r = e.warp; r < e.rows; r += THREADS / 32) {
-      const float4 v = *reinterpret_cast<const float4*>(trow + c);
-      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (EPI == EPI_DACT || EPI == EPI_HEAD) {
-        if (e.vec_aux) av = __ldg(reinterpret_cast<const float4*>(arow + c));
-        else { av.x = __ldg(arow + c); av.y = __ldg(arow + c + 1); av.z = __ldg(arow + c + 2); av.w = __ldg(arow + c + 3); }
+    // Rows in batches of U: all aux loads (Y for the head product, the stored activation for DACT) of a batch are issued before
+    // the first is used.  With two rows in flight the head product spent 35 % of its stall samples on the one FADD that
+    // consumes the Y load (ncu source view): the epilogue, half of that kernel's instructions, was a chain of L2 latencies.
+    constexpr int U = (EPI == EPI_DACT || EPI == EPI_HEAD) ? 8 : 2;
+    constexpr int RS = THREADS / 32;
+    for (int r0 = e.warp; r0 < e.rows; r0 += RS * U) {
+      float4 av[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((EPI == EPI_DACT || EPI == EPI_HEAD) && r0 + RS * u < e.rows) {
+          const float* ar = arow + u * e.a_step;
+          if (e.vec_aux) av[u] = __ldg(reinterpret_cast<const float4*>(ar + c));
+          else { av[u].x = __ldg(ar + c); av[u].y = __ldg(ar + c + 1); av[u].z = __ldg(ar + c + 2); av[u].w = __ldg(ar + c + 3); }
+        }
       }
-      float4 o;
-      o.x = apply(v.x, bv.x, av.x);
-      o.y = nv > 1 ? apply(v.y, bv.y, av.y) : 0.0f;
-      o.z = nv > 2 ? apply(v.z, bv.z, av.z) : 0.0f;
-      o.w = nv > 3 ? apply(v.w, bv.w, av.w) : 0.0f;
-      *reinterpret_cast<float4*>(crow + c) = o;
-      trow += (THREADS / 32) * TILE_LD;
-      crow += e.c_step;
-      arow += e.a_step;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r0 + RS * u < e.rows) {
+          const float4 v = *reinterpret_cast<const float4*>(trow + u * RS * TILE_LD + c);
+          float4 o;
+          o.x = apply(v.x, bv.x, av[u].x);
+          o.y = nv > 1 ? apply(v.y, bv.y, av[u].y) : 0.0f;
+          o.z = nv > 2 ? apply(v.z, bv.z, av[u].z) : 0.0f;
+          o.w = nv > 3 ? apply(v.w, bv.w, av[u].w) : 0.0f;
+          *reinterpret_cast<float4*>(crow + u * e.c_step + c) = o;
+        }
+      }
+      trow += U * RS * TILE_LD;
+      crow += U * e.c_step;
+      arow += U * e.a_step;
     }
   } else {
     float bias_v[4] = {0.f, 0.f, 0.f, 0.f};
