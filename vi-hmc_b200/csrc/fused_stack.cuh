@@ -230,6 +230,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
       tc::mma_commit(bar_mma);
     }
     if (!VIHMC_FUSED_DIRECT_STORE && l >= 1) store_acts(l - 1);   // reads the operand tiles while the tensor core reads them too
+    // this thread's 32 bias values, fetched while the tensor core works (they were the first consumer after the TMEM loads
+    // of every 8-column group: four exposed L2 latencies per layer)
+    float4 bpre[8];
+    {
+      const float* __restrict__ bias = Wc + a.b_off[l];
+      const int nb = (warp >> 2) * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        bpre[i] = nb + 4 * i < N ? __ldg(reinterpret_cast<const float4*>(bias + nb + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     tc::mbar_wait(bar_mma, ph);   // accumulators complete; operand and weight tiles are free
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();              // every thread is done reading the operand tiles (store_acts)
@@ -239,7 +249,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
       const int row = q * 32 + lane;
       unsigned char* prow = A_hi + (row >> 3) * RG_BYTES + (row & 7) * 16;
       const bool last = l == a.n_layers - 1;
-      const float* __restrict__ bias = Wc + a.b_off[l];   // padded layout: 16-byte aligned, length padded to 4
       const long long grow = r0 + row;
       float* __restrict__ orow = a.acts[l] + (c * a.R + grow) * N;
 #pragma unroll
@@ -255,8 +264,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
                      : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
                      : "r"(taddr + 128u));
         const bool two = n + 4 < N;   // widths are multiples of 4: the second float4 of the group is all in or all out
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-        const float4 b1 = two ? __ldg(reinterpret_cast<const float4*>(bias + n + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b0 = bpre[cc >> 2], b1 = bpre[(cc >> 2) + 1];
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float v[8];
