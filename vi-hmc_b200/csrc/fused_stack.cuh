@@ -251,40 +251,52 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_forward_kernel(FusedFwdArg
       const bool last = l == a.n_layers - 1;
       const long long grow = r0 + row;
       float* __restrict__ orow = a.acts[l] + (c * a.R + grow) * N;
+      // two 16-column halves: the four TMEM loads (main + correction accumulator of two 8-column groups) of a half are in
+      // flight together behind ONE tcgen05.wait::ld instead of one wait per group
 #pragma unroll
-      for (int cc = 0; cc < 32; cc += 8) {
-        const int n = cq4 * 32 + cc;
-        if (n >= N) break;
-        uint32_t r[8], rc[8];
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(taddr));
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
-                     : "r"(taddr + 128u));
-        const bool two = n + 4 < N;   // widths are multiples of 4: the second float4 of the group is all in or all out
-        const float4 b0 = bpre[cc >> 2], b1 = bpre[(cc >> 2) + 1];
+      for (int hh = 0; hh < 2; ++hh) {
+        const int nh = cq4 * 32 + hh * 16;
+        if (nh >= N) break;
+        uint32_t r[2][8], rc[2][8];
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(nh + 8 * g2);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r[g2][0]), "=r"(r[g2][1]), "=r"(r[g2][2]), "=r"(r[g2][3]), "=r"(r[g2][4]), "=r"(r[g2][5]), "=r"(r[g2][6]),
+                         "=r"(r[g2][7])
+                       : "r"(taddr));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(rc[g2][0]), "=r"(rc[g2][1]), "=r"(rc[g2][2]), "=r"(rc[g2][3]), "=r"(rc[g2][4]), "=r"(rc[g2][5]),
+                         "=r"(rc[g2][6]), "=r"(rc[g2][7])
+                       : "r"(taddr + 128u));
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]) + bb[j];
-          v[j] = last ? x : activate<ACT>(x);
-        }
-        if (VIHMC_FUSED_DIRECT_STORE && grow < a.R) {
-          *reinterpret_cast<float4*>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          if (two) *reinterpret_cast<float4*>(orow + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        float4 hi, lo;
-        tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
-        *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = hi;
-        *reinterpret_cast<float4*>(prow + A_TILE + (n >> 2) * 128) = lo;
-        if (two) {
-          tc::split4(make_float4(v[4], v[5], v[6], v[7]), hi, lo);
-          *reinterpret_cast<float4*>(prow + ((n >> 2) + 1) * 128) = hi;
-          *reinterpret_cast<float4*>(prow + A_TILE + ((n >> 2) + 1) * 128) = lo;
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const int n = nh + 8 * g2, cc = hh * 16 + 8 * g2;
+          if (n >= N) break;
+          const bool two = n + 4 < N;   // widths are multiples of 4: the second float4 of the group is all in or all out
+          const float4 b0 = bpre[cc >> 2], b1 = bpre[(cc >> 2) + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = __uint_as_float(r[g2][j]) + __uint_as_float(rc[g2][j]) + bb[j];
+            v[j] = last ? x : activate<ACT>(x);
+          }
+          if (VIHMC_FUSED_DIRECT_STORE && grow < a.R) {
+            *reinterpret_cast<float4*>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (two) *reinterpret_cast<float4*>(orow + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          float4 hi, lo;
+          tc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+          *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = hi;
+          *reinterpret_cast<float4*>(prow + A_TILE + (n >> 2) * 128) = lo;
+          if (two) {
+            tc::split4(make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+            *reinterpret_cast<float4*>(prow + ((n >> 2) + 1) * 128) = hi;
+            *reinterpret_cast<float4*>(prow + A_TILE + ((n >> 2) + 1) * 128) = lo;
+          }
         }
       }
       // a narrower layer leaves stale columns [N, K) of the previous one in the tiles: clear them (never taken at equal widths)
@@ -418,23 +430,33 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_backward_kernel(FusedBwdAr
       const int row = q * 32 + lane;
       unsigned char* prow = A_hi + (row >> 3) * RG_BYTES + (row & 7) * 16;
 #pragma unroll
-      for (int cc = 0; cc < 32; cc += 8) {
-        const int n = cq4 * 32 + cc;
-        if (n >= N) break;
-        uint32_t r[8], rc[8];
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(taddr));
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
-                     : "r"(taddr + 128u));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float v[8];
+      for (int hh = 0; hh < 2; ++hh) {   // two 16-column halves, four TMEM loads behind one wait (as in the forward kernel)
+        const int nh = cq4 * 32 + hh * 16;
+        if (nh >= N) break;
+        uint32_t r[2][8], rc[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-        *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = make_float4(v[0], v[1], v[2], v[3]);
-        if (n + 4 < N) *reinterpret_cast<float4*>(prow + ((n >> 2) + 1) * 128) = make_float4(v[4], v[5], v[6], v[7]);
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(nh + 8 * g2);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r[g2][0]), "=r"(r[g2][1]), "=r"(r[g2][2]), "=r"(r[g2][3]), "=r"(r[g2][4]), "=r"(r[g2][5]), "=r"(r[g2][6]),
+                         "=r"(r[g2][7])
+                       : "r"(taddr));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(rc[g2][0]), "=r"(rc[g2][1]), "=r"(rc[g2][2]), "=r"(rc[g2][3]), "=r"(rc[g2][4]), "=r"(rc[g2][5]),
+                         "=r"(rc[g2][6]), "=r"(rc[g2][7])
+                       : "r"(taddr + 128u));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const int n = nh + 8 * g2;
+          if (n >= N) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g2][j]) + __uint_as_float(rc[g2][j]);
+          *reinterpret_cast<float4*>(prow + (n >> 2) * 128) = make_float4(v[0], v[1], v[2], v[3]);
+          if (n + 4 < N) *reinterpret_cast<float4*>(prow + ((n >> 2) + 1) * 128) = make_float4(v[4], v[5], v[6], v[7]);
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
