@@ -875,7 +875,7 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
   // TMEM-A variant: plain-store products with one n-tile of at most 112 columns and a vector-staged B (the weight-gradient
   // GEMMs and the two head-backward products).  VIHMC_TC_TMEMA=0 keeps the shared-memory A path.
   static const bool atm_on = []() { const char* e = getenv("VIHMC_TC_TMEMA"); return e == nullptr || atoi(e) != 0; }();
-  const bool use_atm = EPI == EPI_STORE && atm_on && g.N <= tc::ATM_ACCN && b_mode != tc::LOAD_SCALAR;
+  const bool use_atm = EPI == EPI_STORE && atm_on && g.N <= tc::ATM_ACCN;
   g.splits = 1;
   g.batch = batch;
   if (EPI == EPI_STORE && scratch != nullptr && g.K > kSplitKThreshold) {
@@ -915,18 +915,21 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
   dim3 grid(tiles_n, tiles_m, batch * g.splits);
   if (EPI == EPI_STORE && use_atm) {
     using KernelT = void (*)(GemmArgs, int, int);
-    static const KernelT table[3][2] = {
-        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_KVEC>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_MNVEC>},
-        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_KVEC>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_MNVEC>},
-        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_KVEC>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_MNVEC>}};
+    static const KernelT table[3][3] = {
+        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_SCALAR>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_KVEC>,
+         tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_SCALAR, tc::LOAD_MNVEC>},
+        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_SCALAR>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_KVEC>,
+         tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_KVEC, tc::LOAD_MNVEC>},
+        {tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_SCALAR>, tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_KVEC>,
+         tc::tc_gemm_kernel<EPI_STORE, true, tc::LOAD_MNVEC, tc::LOAD_MNVEC>}};
     static bool configured_atm = false;
     if (!configured_atm) {
       for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 3; ++j)
           VIHMC_CUDA_OK(cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
       configured_atm = true;
     }
-    table[a_mode][b_mode - 1]<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+    table[a_mode][b_mode]<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
   } else if (a_mode == tc::LOAD_KVEC && b_mode == tc::LOAD_KVEC) {
     // both operands K-contiguous and aligned (the head product, the wide-MLP layers): staging modes fixed at compile time
     auto kk = tc::tc_gemm_kernel<EPI, false, tc::LOAD_KVEC, tc::LOAD_KVEC>;
