@@ -120,16 +120,44 @@ __device__ __forceinline__ float act_fwd(int act, float z, float& dact) {
   }
 }
 
-// tanh(x) = sign(x) (1 - 2 / (2^(|x| * 2 log2 e) + 1)) on ex2.approx / rcp.approx: 6 instructions (FMUL, MUFU.EX2, FADD,
-// MUFU.RCP, FFMA, LOP3), no branch; e = +inf for large |x| gives rcp = 0 and tanh = +-1 exactly.
-// Absolute error <= ~1.2e-7 (one ulp at 1.0) over the whole range -- the same as tanhf's large-|x|
-// branch; near 0 the RELATIVE error grows like 6e-8/|x|, which is harmless here because activations only
-// ever enter sums against O(1) terms (checked by the rtol-1e-5 parity tests against the reference).
+// tanh(x) = 1 - 2 / (2^(x * 2 log2 e) + 1) on ex2.approx / rcp.approx: 5 instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA), no
+// branch, no sign handling: e = +inf for large x gives rcp = 0 and tanh = 1, e = 0 (flushed) for large -x gives 1 - 2 = -1.
+// Absolute error <= ~1.2e-7 (one ulp at 1.0) over the whole range -- the same as tanhf's large-|x| branch; near 0 the
+// RELATIVE error grows like 6e-8/|x|, which is harmless here because activations only ever enter sums against O(1) terms
+// (checked by the rtol-1e-5 parity tests against the reference).  The result is odd in x only to that accuracy.
 __device__ __forceinline__ float tanh_sel(float x) {
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.885390081777927f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-  return copysignf(fmaf(-2.0f, r, 1.0f), x);
+  return fmaf(-2.0f, r, 1.0f);
+}
+
+// packed FP32 pairs (Blackwell FFMA2: one instruction, two IEEE fma.rn results)
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// two tanh_sel at once: the three FP32 steps on the packed pipe (7 instructions per pair instead of 10); every step is the
+// same IEEE operation as in tanh_sel (x * c = fma(x, c, 0), e + 1 = fma(e, 1, 1)), so the results are bit-identical to it
+__device__ __forceinline__ unsigned long long tanh_sel2(unsigned long long x) {
+  const unsigned long long c = pack_f2(2.885390081777927f, 2.885390081777927f), one = pack_f2(1.0f, 1.0f), m2 = pack_f2(-2.0f, -2.0f);
+  float a0, a1, e0, e1, r0, r1;
+  unpack_f2(fma_f2(x, c, 0ull), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  unpack_f2(fma_f2(pack_f2(e0, e1), one, one), a0, a1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(a0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(a1));
+  return fma_f2(pack_f2(r0, r1), m2, one);
 }
 
 // Gaussian likelihood pieces (main_VI_HMC.py:132-136; GaussianNLLLoss clamps var at 1e-6, full=False)

@@ -597,8 +597,12 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const float w = sm[L.wbase[0] + (j0 + u * JP) * L.ws[0]], b = sm[L.bbase[0] + j0 + u * JP];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) h0[u][t] = tanh_sel(fmaf(w, F.x[t], b));
+      // fmaf(w, x, b) and the tanh on packed pairs: the same IEEE operations as the scalar forms, two per instruction
+      {
+        const unsigned long long w2 = pack_f2(w, w), b2 = pack_f2(b, b);
+        unpack_f2(tanh_sel2(fma_f2(w2, pack_f2(F.x[0], F.x[1]), b2)), h0[u][0], h0[u][1]);
+        unpack_f2(tanh_sel2(fma_f2(w2, pack_f2(F.x[2], F.x[3]), b2)), h0[u][2], h0[u][3]);
+      }
       if (ln.unit) store8(act + L.h + (j0 + u * JP) * NCS + n0, h0[u]);
     }
   }
@@ -613,8 +617,8 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
     dot_rows_2x4<W, NCS>(sm + L.wbase[1] + j0 * WSW, act + L.h + n0, h1);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-#pragma unroll
-      for (int t = 0; t < 4; ++t) h1[u][t] = tanh_sel(h1[u][t]);
+      unpack_f2(tanh_sel2(pack_f2(h1[u][0], h1[u][1])), h1[u][0], h1[u][1]);
+      unpack_f2(tanh_sel2(pack_f2(h1[u][2], h1[u][3])), h1[u][2], h1[u][3]);
       if (ln.unit) store8(act + L.h + (W + j0 + u * JP) * NCS + n0, h1[u]);
     }
   }
@@ -639,8 +643,17 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
     for (int u = 0; u < 2; ++u) {
       const float wo = sm[L.wbase[2] + j0 + u * JP];
       float dz[4];
+      {  // dz = (wo * dO) * (1 - h1^2), packed: mul = fma(., ., 0) would turn -0 into +0, so the products use mul.rn.f32x2
+        const unsigned long long one = pack_f2(1.0f, 1.0f), wo2 = pack_f2(wo, wo);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) dz[t] = wo * dO[t] * fmaf(-h1[u][t], h1[u][t], 1.0f);
+        for (int t = 0; t < 4; t += 2) {
+          const unsigned long long h = pack_f2(h1[u][t], h1[u][t + 1]), nh = pack_f2(-h1[u][t], -h1[u][t + 1]);
+          unsigned long long p, q;
+          asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(wo2), "l"(pack_f2(dO[t], dO[t + 1])));
+          asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(p), "l"(fma_f2(nh, h, one)));
+          unpack_f2(q, dz[t], dz[t + 1]);
+        }
+      }
       if (ln.unit) store8(act + L.dz + (W + j0 + u * JP) * NCS + n0, dz);
     }
   }
@@ -654,8 +667,16 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
     dot_rows_2x4<W, NCS>(sm + L.tbase[1] + j0 * WSW, act + L.dz + W * NCS + n0, acc);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
+      {
+        const unsigned long long one = pack_f2(1.0f, 1.0f);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) acc[u][t] *= fmaf(-h0[u][t], h0[u][t], 1.0f);
+        for (int t = 0; t < 4; t += 2) {
+          const unsigned long long h = pack_f2(h0[u][t], h0[u][t + 1]), nh = pack_f2(-h0[u][t], -h0[u][t + 1]);
+          unsigned long long q;
+          asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(pack_f2(acc[u][t], acc[u][t + 1])), "l"(fma_f2(nh, h, one)));
+          unpack_f2(q, acc[u][t], acc[u][t + 1]);
+        }
+      }
       if (ln.unit) store8(act + L.dz + (j0 + u * JP) * NCS + n0, acc[u]);
     }
   }
