@@ -625,8 +625,14 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
   __syncwarp();
   float ll_lane = 0.0f;
   if (ct < NC) {  // output layer + Gaussian residual, lane = data point
-    const float* wo = sm + L.wbase[2];
-    const float* hl = act + L.h + W * NCS + ct;
+    const float4* wo4 = reinterpret_cast<const float4*>(sm + L.wbase[2]);   // the output row, padded to WSW floats: three broadcast
+    const float* hl = act + L.h + W * NCS + ct;                            // LDS.128 instead of W scalar ones
+    float wo[WSW];
+#pragma unroll
+    for (int k4 = 0; k4 < WSW / 4; ++k4) {
+      const float4 v = wo4[k4];
+      wo[4 * k4] = v.x; wo[4 * k4 + 1] = v.y; wo[4 * k4 + 2] = v.z; wo[4 * k4 + 3] = v.w;
+    }
     float o = sm[L.bbase[2]];
 #pragma unroll
     for (int k = 0; k < W; ++k) o = fmaf(wo[k], hl[k * NCS], o);
