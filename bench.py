@@ -325,8 +325,9 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
                      "note": "neither hbm nor tensor: 20x10x10 tiles are below any UMMA shape and all state lives in "
                              "shared memory; peak = 148 SM x 128 FMA lanes x 2 x sm_max_mhz (computed, not in "
                              "MEASURED_PEAKS.json); achieved = 14 kFLOP per chain-grad-eval (SURVEY 8(d)) / event time. "
-                             "ncu (profiles/r01_summary.md): the binding unit is the shared-memory pipe, "
-                             "l1tex lsu shared wavefronts 76 % of peak, 527 warp instructions per evaluation"},
+                             "ncu (profiles/r01_ncu_details_mlp_small_sample_final2.csv, profiles/r01_summary.md): the binding unit is "
+                             "the shared-memory pipe, l1tex lsu shared wavefronts 78 % of peak (303 per evaluation), 447 warp "
+                             "instructions per evaluation, issue slots 29 % busy; DRAM 217 KB read / 0 written per 40-iteration launch"},
         "cpu_baseline": cpu_baseline_leg() if (world == 1 and not skip_cpu) else None,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
                 "seconds": e2e_s},
