@@ -141,8 +141,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // or becomes NaN, and the sampler rejects either).
 __device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 // The split in the staging loops: TWO packed instructions per element instead of five.  These kernels are bound by instruction
-// issue (with the loads removed a long-K product still takes 60 % of its time, with the MMAs removed 85 %: tools/bench_gemm_shapes.py
-// on the VIHMC_DBG_* builds), and the split was half of a thread's instructions per k-tile.
+// issue (ncu source view of a long-K product: 242 warp instructions per warp per k-tile, half of them indexing, an eighth the split;
+// profiles/r01_summary.md E1), so every instruction per staged element counts.
 //   hi: Veltkamp's splitter with 2^13 + 1 -- g = fl(8193 v), hi = fl(g + fl(v - g)) is v rounded to nearest at 11 significant bits,
 //       i.e. a tf32 value -- as three fma.rn.f32x2 (Blackwell's packed FP32 pipe: two IEEE results per instruction);
 //   lo: v - hi, exact in fp32, NOT rounded to tf32: the tensor core drops the 13 low mantissa bits of a tf32 operand, a truncation
