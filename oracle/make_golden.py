@@ -159,6 +159,59 @@ def bnn_vi_training_cases():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def deeponet_vi_training_case():
+    """The reference's Bayesian_DeepONet / train_model / validate_model / Adam / ReduceLROnPlateau loop
+    (Operator_network/VI/main_VI_deeponet.py:24-118,:153-165) on the small synthetic Burgers-shaped problem: two mini-batches of
+    functions on a shared trunk grid, loss = NLL(mean) * train_size + beta * KL.  The eps stream is recovered by replaying the global
+    generator (branch layers, trunk layers, then the output bias -- the order the forward pass draws them) and stored in the
+    flat order of the deterministic net (b first)."""
+    m = ref_loader.load_script("Operator_network/VI", "main_VI_deeponet", "ref_don_vi_train")
+    cfg = m.cfg
+    cfg.dataset, cfg.noise_type, cfg.learn_noise = "Burgers", 0, False
+    arch = DeepONetArch(width_branch=16, width_trunk=16, in_branch=12, depth_branch=3, depth_trunk=4, output_neurons=8)
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=6, n_t=5, n_x=7, seed=0)
+    n, P = x1.shape[0], x2.shape[0]
+    half, epochs, num_ens, lr = n // 2, 3, 2, 1e-3
+    priors = {"prior_mu": 0, "prior_sigma": 0.1, "posterior_mu_initial": (0, 0.1), "posterior_rho_initial": (-5, 0.1)}
+    torch.manual_seed(5)
+    model = m.Bayesian_DeepONet(priors, arch.width_branch, arch.width_trunk, arch.in_branch, arch.in_trunk, arch.depth_branch,
+                                arch.depth_trunk, arch.output_neurons, arch.act, 0, 0, impose_bc=True)
+    layers = [l for l in list(model.b1) + list(model.b2) if hasattr(l, "W_mu")]
+
+    def flat(attr_w, attr_b, battr):
+        return torch.cat([getattr(model, battr).detach().flatten()] +
+                         [torch.cat([getattr(l, attr_w).detach().flatten(), getattr(l, attr_b).detach().flatten()]) for l in layers])
+    mu0, rho0 = flat("W_mu", "bias_mu", "b_mu").clone(), flat("W_rho", "bias_rho", "b_rho").clone()
+    batch = lambda lo, hi: (x1[lo:hi].unsqueeze(1), x2.unsqueeze(0).repeat(hi - lo, 1, 1), y[lo:hi])
+    train_loader, valid_loader = [batch(0, half), batch(half, n)], [batch(0, n)]
+    size = float(n * P)
+    opt = m.Adam(model.parameters(), lr=lr)
+    sched = m.lr_scheduler.ReduceLROnPlateau(opt, patience=500, min_lr=1e-5)
+    loss = m.metrics.ELBO(False, 0)
+    noise_param = torch.tensor(1.0)
+    hist, eps_all = [], []
+    for ep in range(epochs):
+        torch.manual_seed(2000 + ep)
+        for b in range(2):
+            for j in range(num_ens):
+                draws = [torch.cat([torch.empty(l.W_mu.size()).normal_(0, 1).flatten(), torch.empty(l.bias_mu.size()).normal_(0, 1)])
+                         for l in layers]
+                b_eps = torch.empty(model.b_mu.size()).normal_(0, 1)
+                eps_all.append(torch.cat([b_eps] + draws))
+        torch.manual_seed(2000 + ep)
+        lr_used = opt.param_groups[0]["lr"]
+        tl = m.train_model(train_loader, model, loss, opt, size, 2, num_ens, 1.0, noise_param=noise_param)
+        vl = m.validate_model(valid_loader, model, loss, size, 1.0, 1, noise_param=noise_param)
+        sched.step(vl)
+        hist.append([tl, vl, lr_used])
+    out = {"mu0": mu0.numpy(), "rho0": rho0.numpy(), "eps": torch.stack(eps_all).reshape(epochs * 2, num_ens, -1).numpy(),
+           "mu": flat("W_mu", "bias_mu", "b_mu").numpy(), "rho": flat("W_rho", "bias_rho", "b_rho").numpy(),
+           "history": np.asarray(hist, np.float64), "cfg": np.asarray([1.0, 0.0, 0.1, 1.0, lr, 500], np.float64)}
+    path = os.path.join(GOLDEN, "deeponet_vi_training.npz")
+    np.savez_compressed(path, **out)
+    print("deeponet VI history", np.asarray(hist), "wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def bnn_vi_hmc_cases():
     """Reference closure Neural_network/VI_HMC/main_VI_HMC.py:28-153 on the bundled data."""
     m = ref_loader.load_bnn_vi_hmc()
@@ -280,3 +333,4 @@ if __name__ == "__main__":
     bnn_sensitivity_cases()
     deeponet_sensitivity_cases()
     bnn_vi_training_cases()
+    deeponet_vi_training_case()

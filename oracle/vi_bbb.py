@@ -66,7 +66,7 @@ def train_batches(batches, valid_batches, forward, mu0, rho0, eps, noise_var, pr
     """The mini-batch form of the loop, Operator_network/VI/main_VI_deeponet.py:56-80 (train) and :105-118 (validate) with
     metrics.py:29-31: loss = gaussian_nll_loss(mean) * train_size + beta * kl per batch, one Adam step per batch, epoch losses =
     means over the batches.  batches: list of (inputs, y); forward(w, inputs) -> prediction shaped like y.  eps [epochs * n_batches,
-    num_ens, D].  (No reference-generated golden vector: the step arithmetic is pinned by the BNN trainer's.)"""
+    num_ens, D].  Pinned by tests/golden/deeponet_vi_training.npz: the reference's own Bayesian_DeepONet training loop on the same eps stream."""
     mu = mu0.to(dtype).clone().requires_grad_()
     rho = rho0.to(dtype).clone().requires_grad_()
     opt = torch.optim.Adam([mu, rho], lr=lr_start)

@@ -133,3 +133,62 @@ def test_cuda_trainer_deeponet_minibatches_vs_restated_loop():
     np.testing.assert_allclose(res.history.numpy()[:, :2], hist[:, :2], rtol=2e-4)
     np.testing.assert_allclose(res.mu.numpy(), mu.numpy(), rtol=1e-3, atol=2e-4)
     np.testing.assert_allclose(res.rho.numpy(), rho.numpy(), rtol=1e-3, atol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# DeepONet form pinned by the reference's own Bayesian_DeepONet training loop (tests/golden/deeponet_vi_training.npz)
+# ------------------------------------------------------------------------------------------------
+def _don_vi_case():
+    g = cases.load_golden("deeponet_vi_training.npz")
+    inp = cases.don_inputs("small")
+    noise_var, prior_mu, prior_sigma, beta, lr, patience = g["cfg"]
+    return g, inp, dict(noise_var=float(noise_var), prior_mu=float(prior_mu), prior_sigma=float(prior_sigma), beta=float(beta),
+                        lr=float(lr), patience=int(patience))
+
+
+def _don_forward(inp):
+    arch = inp["arch"]
+    kw = cases._don_kwargs(arch, torch.float32)
+    slots = cases.oc.deeponet_layout(kw["width_branch"], kw["width_trunk"], kw["in_branch"], kw["in_trunk"], kw["depth_branch"],
+                                     kw["depth_trunk"], kw["output_neurons"])
+    x2 = inp["x2"]
+
+    def forward(w, xb):
+        return cases.oc.deeponet_forward(xb.unsqueeze(1), x2.unsqueeze(0), cases.oc.unflatten(slots, w), kw["depth_branch"],
+                                         kw["depth_trunk"], kw["act"], kw["impose_bc"]).squeeze(1)
+    return forward
+
+
+def test_deeponet_oracle_matches_reference_training_run():
+    g, inp, kw = _don_vi_case()
+    x1, y = inp["x1"], inp["y"]
+    n, P = x1.shape[0], inp["x2"].shape[0]
+    half, size = n // 2, float(n * P)
+    mu, rho, hist = ovi.train_batches([(x1[:half], y[:half]), (x1[half:], y[half:])], [(x1, y)], _don_forward(inp), torch.from_numpy(g["mu0"]),
+                                      torch.from_numpy(g["rho0"]), torch.from_numpy(g["eps"]), kw["noise_var"], kw["prior_mu"],
+                                      kw["prior_sigma"], kw["lr"], kw["patience"], size, size, beta=kw["beta"])
+    np.testing.assert_allclose(hist[:, :2], g["history"][:, :2], rtol=1e-5)
+    np.testing.assert_allclose(mu.numpy(), g["mu"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rho.numpy(), g["rho"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_cuda_trainer_deeponet_matches_reference_training_run(use_graph):
+    from vihmc import vi
+
+    g, inp, kw = _don_vi_case()
+    arch, x1, x2, y = inp["arch"], inp["x1"], inp["x2"], inp["y"]
+    n, P = x1.shape[0], x2.shape[0]
+    half, size = n // 2, float(n * P)
+    mk = lambda a, b: cases.LogProbSpec(arch=arch, x=a, x2=x2, y=b, loss="NLL", tau_out=kw["noise_var"], prior_sigma_scalar=1.0)
+    eps = torch.from_numpy(g["eps"])
+    res = vi.train_bbb([mk(x1[:half], y[:half]), mk(x1[half:], y[half:])], mk(x1, y),
+                       priors=dict(prior_mu=kw["prior_mu"], prior_sigma=kw["prior_sigma"]), lr_start=kw["lr"], lr_patience=kw["patience"],
+                       epochs=eps.shape[0] // 2, num_ens=eps.shape[1], beta=kw["beta"],
+                       nll_scale=[size / (half * P), size / ((n - half) * P)], valid_nll_scale=size / (n * P),
+                       mu0=torch.from_numpy(g["mu0"]), rho0=torch.from_numpy(g["rho0"]), inject_eps=eps, use_graph=use_graph)
+    np.testing.assert_allclose(res.history.numpy()[:, :2], g["history"][:, :2], rtol=2e-4)
+    np.testing.assert_allclose(res.history.numpy()[:, 2], g["history"][:, 2], rtol=1e-6)
+    np.testing.assert_allclose(res.mu.numpy(), g["mu"], rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(res.rho.numpy(), g["rho"], rtol=1e-3, atol=2e-4)
