@@ -388,3 +388,20 @@ def test_minimal_shapes_one_chain_one_coordinate_one_step(force_general):
             ref = hr.sample(closure, q0[0].double(), num_samples=S, num_steps_per_sample=1, step_size=1e-5, momenta=p[:, 0].double(),
                             uniforms=u[:, 0])
             np.testing.assert_allclose(res.samples[:, 0].numpy(), torch.stack(ref).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_validation_step_bnn_regression_and_nll():
+    """main_VI_HMC.py:384-429 (validate): expected MSE per draw from the log-likelihood, both likelihood conventions."""
+    from vihmc import validate
+
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    x, y, xv, yv = cases.synth.bnn_data()
+    for name in ("d40_nll", "d70_regression"):
+        case = cases.bnn_case(g, name)
+        spec = cases.bnn_spec(case)
+        q = torch.from_numpy(case["q"])
+        pred, logp = samplers.predict_model(spec, q, x=xv, y=yv)
+        want = ((pred - yv[None]) ** 2).mean(dim=(1, 2))
+        lp, mse = validate.sample_log_prob_and_mse(spec, q, x=xv, y=yv)
+        np.testing.assert_allclose(mse.numpy(), want.numpy(), rtol=2e-5)
+        np.testing.assert_allclose(lp.numpy(), torch.stack(logp).numpy(), rtol=1e-6)

@@ -315,3 +315,25 @@ def test_fused_stack_kernels_agree_with_the_per_layer_path(tmp_path):
                 _close(res[nofuse][f"{name}/grad"][i], g[f"{name}/full/grad"][i])
         for i in range(res["0"][f"{name}/grad"].shape[0]):
             _close(res["0"][f"{name}/grad"][i], res["1"][f"{name}/grad"][i])
+
+
+def test_validation_step_mse_from_the_log_likelihood_matches_the_predictions(tmp_path):
+    """main_VI_HMC_burgers.py:290-301: per-draw MSE and expected log probability.  vihmc.validate gets the MSE from the value-only
+    log-likelihood kernel (no S x N x P prediction tensor); here it is checked against the predictions themselves."""
+    from vihmc import validate
+
+    inp = cases.don_inputs("small")
+    spec = cases.don_spec(inp, "vi")
+    g = torch.Generator().manual_seed(3)
+    q = inp["mu"][inp["ind"]][None] + 0.02 * torch.randn(7, len(inp["ind"]), generator=g)
+    data = (inp["x1"].unsqueeze(1), inp["x2"].unsqueeze(0), inp["y"])
+    pred, logp = samplers.predict_model(spec, q, data=data)
+    want = ((pred - inp["y"][None]) ** 2).mean(dim=(1, 2))
+    lp, mse = validate.sample_log_prob_and_mse(spec, q, data=data)
+    np.testing.assert_allclose(mse.numpy(), want.numpy(), rtol=2e-5)
+    np.testing.assert_allclose(lp.numpy(), torch.stack(logp).numpy(), rtol=1e-6)
+    out = validate.validate(spec, list(q), burn=2, data=data, out_dir=str(tmp_path), uid="t")
+    saved = np.load(tmp_path / "sample_mse_t.npy")
+    assert saved.shape == (5,) and saved.dtype == np.float32
+    assert out["final_mse"] == pytest.approx(float(want[-1]), rel=2e-5) and out["min_mse"] == pytest.approx(float(want[2:].min()), rel=2e-5)
+    assert out["expected_log_prob"] == pytest.approx(float(torch.stack(logp)[2:].mean()), rel=1e-6)

@@ -5,7 +5,7 @@ hand-written sm_100a CUDA behind the C ABI declared in ``include/vihmc.h`` (``li
 loaded with ctypes).  There is no CPU fallback: anything that computes raises if the library or a
 GPU is missing.
 """
-from . import engine, samplers, spec, synth, util  # noqa: F401
+from . import engine, samplers, spec, synth, util, validate  # noqa: F401
 from .samplers import Integrator, Sampler, predict_model, sample, sample_model  # noqa: F401
 from .spec import DeepONetArch, LogProbSpec, MLPArch  # noqa: F401
 
