@@ -291,6 +291,7 @@ class DeepONetLogProb:
     frozen: Optional[torch.Tensor] = None
     sens_ind: Optional[np.ndarray] = None
     dtype: torch.dtype = torch.float32
+    sample_p: Optional[int] = None   # cfg.sample_data: a fresh random.sample(range(P), cfg.p) of trunk points per call (:127-137)
     slots: List[TensorSlot] = field(init=False)
 
     def __post_init__(self):
@@ -319,9 +320,16 @@ class DeepONetLogProb:
 
     def __call__(self, q: torch.Tensor) -> torch.Tensor:
         l_prior = self._dist.log_prob(q).sum() + torch.zeros_like(q[0], requires_grad=True)
-        out = self.forward(q)
-        assert out.shape == self.y.shape
-        ll = log_likelihood(out, self.y, self.loss, self.tau_out)
+        if self.sample_p is not None:
+            import random
+            ind = random.sample(range(self.x2.shape[1]), self.sample_p)
+            out = self.forward(q, data=(self.x1, self.x2[:, ind]))
+            y = self.y[:, ind]
+        else:
+            out = self.forward(q)
+            y = self.y
+        assert out.shape == y.shape
+        ll = log_likelihood(out, y, self.loss, self.tau_out)
         return ll + l_prior / self.prior_scale
 
 

@@ -16,11 +16,12 @@ Captured names mirrored (reference file:line)
                                                     Operator_network/VI_HMC/main_VI_HMC_burgers.py:67-180
     object    depth_branch, depth_trunk, act, impose_bc, model, learned_mus, learned_sigmas, sampled_weights,
               sensitive_ind                         Operator_network/VI_HMC/my_make_func.py:14-31
-    globals   cfg.load_prior, cfg.sample_data       main_VI_HMC.py:87,104; main_VI_HMC_burgers.py:76,100,127
+    globals   cfg.load_prior, cfg.sample_data, cfg.p main_VI_HMC.py:87,104; main_VI_HMC_burgers.py:76,100,127-137 (from random import sample :14)
 """
 from __future__ import annotations
 
 import types
+from random import sample
 
 import numpy as np
 import torch
@@ -38,7 +39,7 @@ _ACT_FUNCS = {"tanh": F.tanh, "relu": F.relu}
 _ACT_MODULES = {"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU, "sine": Sin}
 
 # the factories read this module-level name exactly as the reference reads ``import config as cfg``
-cfg = types.SimpleNamespace(load_prior=False, sample_data=False)
+cfg = types.SimpleNamespace(load_prior=False, sample_data=False, p=None)
 
 
 def mlp_module(in_dim=1, widths=(10, 10), out_dim=1, act="tanh", bias=True) -> torch.nn.Module:
@@ -150,7 +151,12 @@ def deeponet_closure(model, model_loss, tr_data, tau_list, tau_out, predict=Fals
     def log_prob_func(params, *args):
         l_prior = dist_list[0].log_prob(params).sum() + torch.zeros_like(params[0], requires_grad=True)
         x1, x2, y = tr_data
-        output = fmodel(x1, x2, parameters=params).squeeze(1)
+        if predict or not cfg.sample_data:
+            output = fmodel(x1, x2, parameters=params).squeeze(1)
+        else:   # main_VI_HMC_burgers.py:127-137
+            ind = sample(range(x2.shape[1]), cfg.p)
+            output = fmodel(x1, x2[:, ind], parameters=params).squeeze(1)
+            y = y[:, ind]
         assert output.shape == y.shape
         if model_loss == 'NLL':
             ll = - nll_loss(output, y, tau_out * torch.ones_like(output))

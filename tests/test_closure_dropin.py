@@ -134,12 +134,26 @@ def test_deeponet_vi_reference_closure_recovers_to_the_factory_spec():
     q = mu[ind] + 0.01 * torch.randn(len(ind))
     (l1, g1), (l2, g2) = _grad(fn, q), _grad(fn2, q)
     assert l1 == l2 and torch.equal(g1, g2)
-    cfg.sample_data = True
+    # cfg.sample_data: the recovered specification carries cfg.p, and the closure's value on its random subset equals the oracle's
+    # on the same subset (both draw it from Python's global generator)
+    import random
+    cfg.sample_data, old_p = True, getattr(cfg, "p", None)
+    cfg.p = 9
     try:
-        with pytest.raises(NotImplementedError, match="sample_data"):
-            closure.spec_from_closure(fn)
+        sub = closure.spec_from_closure(fn)
+        assert sub.trunk_subsample == 9
+        assert_specs_equal(dataclasses.replace(sub, trunk_subsample=None), want)
+        oracle = cases.oc.DeepONetLogProb(x1=tr_data[0], x2=tr_data[1], y=tr_data[2], frozen=mu, sens_ind=ind, sample_p=9,
+                                          **cases._don_kwargs(arch, torch.float32))
+        random.seed(4)
+        a = _grad(fn, q)
+        random.seed(4)
+        b = _grad(oracle, q)
+        assert a[0] == b[0] and torch.equal(a[1], b[1])
+        random.seed(5)
+        assert _grad(fn, q)[0] != a[0]          # another subset, another value
     finally:
-        cfg.sample_data = False
+        cfg.sample_data, cfg.p = False, old_p
 
 
 @needs_reference

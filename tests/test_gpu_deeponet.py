@@ -337,3 +337,41 @@ def test_validation_step_mse_from_the_log_likelihood_matches_the_predictions(tmp
     assert saved.shape == (5,) and saved.dtype == np.float32
     assert out["final_mse"] == pytest.approx(float(want[-1]), rel=2e-5) and out["min_mse"] == pytest.approx(float(want[2:].min()), rel=2e-5)
     assert out["expected_log_prob"] == pytest.approx(float(torch.stack(logp)[2:].mean()), rel=1e-6)
+
+
+def test_trunk_subsampling_closure_calls_match_the_restated_sampler():
+    """cfg.sample_data (main_VI_HMC_burgers.py:127-137): every closure call -- 2 Hamiltonians + L + 1 gradients per iteration --
+    redraws cfg.p trunk points from Python's global generator.  The engine composes the iteration on the host from its building
+    blocks; with the same random.seed, injected momenta and uniforms it must follow the restated hamiltorch sampler running the
+    oracle closure (same subsets in the same order), accept / reject included."""
+    import dataclasses
+    import random
+
+    inp = cases.don_inputs("small")
+    spec = dataclasses.replace(cases.don_spec(inp, "vi"), trunk_subsample=9)
+    arch = inp["arch"]
+    d, S, L, eps = spec.d, 5, 3, 1e-4
+    rs = np.random.RandomState(3)
+    q0 = inp["mu"][inp["ind"]].clone()
+    p = torch.from_numpy(rs.randn(S, 1, d).astype(np.float32))
+    p[2] *= 30.0                                   # one overshooting trajectory
+    u = torch.from_numpy(rs.uniform(0.2, 1.0, size=(S, 1)).astype(np.float32))
+    random.seed(11)
+    res = samplers.sample(spec, q0, num_samples=S, num_steps_per_sample=L, step_size=eps, burn=1, inject_momenta=p, inject_uniforms=u,
+                          return_result=True)
+    oracle = cases.oc.DeepONetLogProb(x1=inp["x1"].unsqueeze(1), x2=inp["x2"].unsqueeze(0), y=inp["y"], frozen=inp["mu"],
+                                      sens_ind=inp["ind"], sample_p=9, **cases._don_kwargs(arch, torch.float64))
+    random.seed(11)
+    trace = {}
+    ref = hr.sample(oracle, q0.double(), num_samples=S, num_steps_per_sample=L, step_size=eps, burn=1, momenta=p[:, 0].double(),
+                    uniforms=u[:, 0], trace=trace)
+    assert res.samples.shape == (S - 1, 1, d)
+    np.testing.assert_allclose(res.hamiltonians[:, 0, 0].numpy(), trace["H0"], rtol=1e-5)
+    np.testing.assert_allclose(res.hamiltonians[:, 0, 1].numpy(), trace["H1"], rtol=1e-5)
+    assert [bool(a) for a in res.accepted[:, 0]] == trace["accept"]
+    np.testing.assert_allclose(res.samples[:, 0].numpy(), torch.stack(ref).numpy(), rtol=1e-4, atol=1e-5)
+    # a different seed of the global generator gives different subsets, hence different Hamiltonians
+    random.seed(12)
+    res2 = samplers.sample(spec, q0, num_samples=2, num_steps_per_sample=L, step_size=eps, inject_momenta=p[:2], inject_uniforms=u[:2],
+                           return_result=True)
+    assert not np.allclose(res2.hamiltonians[0, 0].numpy(), res.hamiltonians[0, 0].numpy(), rtol=1e-7)

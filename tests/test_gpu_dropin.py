@@ -131,3 +131,27 @@ def test_sample_model_and_predict_model_entry_points_of_the_shim():
     for s, o, lp in zip(samples[2:], pred, logp):
         np.testing.assert_allclose(o.numpy(), oracle.forward(s).detach().numpy(), rtol=1e-5, atol=1e-5)
         assert float(lp) == pytest.approx(float(oracle(s).detach()), rel=1e-5)
+
+
+def test_subsampling_closure_through_the_shim():
+    """cfg.sample_data = True in the reference's config: the closure redraws cfg.p trunk points per call.  Through the shim the
+    set-up check replays the closure's subset for the engine (and leaves Python's generator untouched), then the run follows the
+    specification path draw for draw."""
+    import random
+
+    import hamiltorch
+
+    inp, net, tr, tau_list = _don_closures()
+    rshape.cfg.sample_data, rshape.cfg.p = True, 9
+    try:
+        fn = rshape.deeponet_closure(net, "NLL", tr, tau_list, 1.0, mean_params=inp["mu"], std_params=inp["sigma"], grad_ind=inp["ind"])
+        spec = closure.spec_from_closure(fn)
+        assert spec.trunk_subsample == 9
+        q0 = inp["mu"][inp["ind"]].clone()
+        random.seed(21)
+        out = hamiltorch.samplers.sample(fn, q0, num_samples=4, num_steps_per_sample=3, step_size=1e-4, seed=6)
+        random.seed(21)
+        want = samplers.sample(spec, q0, num_samples=4, num_steps_per_sample=3, step_size=1e-4, seed=6)
+        assert torch.equal(torch.stack(out), torch.stack(want))
+    finally:
+        rshape.cfg.sample_data, rshape.cfg.p = False, None

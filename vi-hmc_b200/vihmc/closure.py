@@ -108,6 +108,7 @@ def spec_from_closure(fn) -> LogProbSpec:
         vi_sigma = None if sig is None else _cpu(sig)
 
     is_deeponet = hasattr(owner, "depth_branch")
+    trunk_subsample = None
     if is_deeponet:
         base = DeepONetArch.from_module(model)
         arch = DeepONetArch(width_branch=base.width_branch, width_trunk=base.width_trunk, in_branch=base.in_branch,
@@ -116,9 +117,10 @@ def spec_from_closure(fn) -> LogProbSpec:
                             impose_bc=bool(getattr(owner, "impose_bc", True)))
         if "tr_data" not in fv:
             raise ClosureError("DeepONet closure without captured tr_data")
-        if not predict and bool(getattr(cfg, "sample_data", False)):
-            raise NotImplementedError("cfg.sample_data (a fresh random.sample of trunk points per closure call, "
-                                      "main_VI_HMC_burgers.py:127-137) is not on the accelerated path; shipped configs leave it off")
+        # cfg.sample_data: a fresh random.sample(range(P), cfg.p) of the trunk points per closure call (main_VI_HMC_burgers.py:127-137);
+        # only closures whose body reads cfg.sample_data have it (the full-HMC drivers do not)
+        if not predict and "sample_data" in fn.__code__.co_names and bool(getattr(cfg, "sample_data", False)):
+            trunk_subsample = int(cfg.p)
         x1, x2, y = fv["tr_data"]
         x, x2, y = _cpu(x1).reshape(x1.shape[0], -1), _cpu(x2).reshape(-1, x2.shape[-1]), _cpu(y)
     else:
@@ -153,7 +155,7 @@ def spec_from_closure(fn) -> LogProbSpec:
     tau_out = fv["tau_out"]
     spec = LogProbSpec(arch=arch, x=x, x2=x2, y=y, loss=fv["model_loss"], tau_out=float(tau_out), prior_mu=prior_mu,
                        prior_sigma=prior_sigma, prior_sigma_scalar=scal, prior_scale=float(fv.get("prior_scale", 1.0)),
-                       frozen=frozen, sens_ind=sens_ind, vi_sigma=vi_sigma, predict=predict)
+                       frozen=frozen, sens_ind=sens_ind, vi_sigma=vi_sigma, predict=predict, trunk_subsample=trunk_subsample)
     spec.validate()
     return spec
 
@@ -176,12 +178,22 @@ def verify_closure(fn, spec: LogProbSpec, q: torch.Tensor, rtol: float = 1e-4, p
         if torch.is_tensor(v):
             dev = v.device
             break
+    import random
+
+    rstate = random.getstate()   # a subsampling closure draws its trunk subset from Python's global generator: replay it for the engine
     p = q.to(dev).clone().requires_grad_()
     out = fn(p)
     lp = (out[0] if isinstance(out, tuple) else out).sum()
     (g,) = torch.autograd.grad(lp, p)
     lp_ref, g_ref = float(lp.detach()), g.detach().cpu()
-    lp_eng, g_eng = engine.logp_grad(prepared if prepared is not None else spec, q.reshape(1, -1).cpu())
+    if spec.trunk_subsample is not None:
+        random.setstate(rstate)
+        prep = engine.prepare(prepared if prepared is not None else spec)
+        sub = engine._TrunkSubset(prep, random.sample(range(spec.P), int(spec.trunk_subsample)))
+        lp_eng, g_eng = sub.logp_grad(engine._to_dev(q.reshape(1, -1), prep.device))
+        random.setstate(rstate)   # the check leaves the generator where the caller had it
+    else:
+        lp_eng, g_eng = engine.logp_grad(prepared if prepared is not None else spec, q.reshape(1, -1).cpu())
     lp_eng, g_eng = float(lp_eng.reshape(-1)[0]), g_eng.reshape(-1).cpu()
     err_lp = abs(lp_eng - lp_ref) / max(abs(lp_ref), 1e-30)
     scale = max(float(g_ref.abs().max()), 1e-30)

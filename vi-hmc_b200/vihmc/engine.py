@@ -263,6 +263,95 @@ def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: 
     return res
 
 
+class _TrunkSubset:
+    """The problem of a DeepONet spec restricted to a subset of its trunk points: x2 rows and y columns gathered on the device,
+    the other pointers shared with the parent Prepared (main_VI_HMC_burgers.py:127-137)."""
+
+    def __init__(self, prep: Prepared, ind: Sequence[int]):
+        self.parent = prep
+        idx = torch.as_tensor(np.asarray(ind, dtype=np.int64), device=prep.device)
+        self.x2 = prep.x2.index_select(0, idx).contiguous()
+        self.y = prep.y.index_select(1, idx).contiguous()
+        p = _lib.Problem.from_buffer_copy(prep.problem)
+        p.x2, p.y, p.P = self.x2.data_ptr(), self.y.data_ptr(), int(idx.numel())
+        self.problem = p
+
+    def logp_grad(self, q: torch.Tensor, need_grad: bool = True):
+        prep = self.parent
+        dev = prep.device
+        Cn = q.shape[0]
+        logp = torch.empty(Cn, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(q) if need_grad else None
+        ws = prep.workspace(Cn)   # sized for the full grid: large enough for any subset
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().vihmc_logp_grad(C.byref(self.problem), Cn, q.data_ptr(), logp.data_ptr(), _ptr(grad), ws.data_ptr(),
+                                                   ws.numel(), _stream(dev)))
+        return logp, grad
+
+
+def run_sampler_trunk_subsample(spec, q0: torch.Tensor, num_samples: int, num_steps: int, step_size: float, burn: int = 0,
+                                seed: int = 0, chain_offset: int = 0, inject_momenta: Optional[torch.Tensor] = None,
+                                inject_uniforms: Optional[torch.Tensor] = None, to_host: bool = True) -> SampleResult:
+    """HMC for a DeepONet closure with cfg.sample_data: EVERY closure call -- the two Hamiltonians and the L + 1 gradients of an
+    iteration, L + 3 calls as hamiltorch makes them -- sees a fresh ``random.sample(range(P), p)`` of the trunk points
+    (Operator_network/VI_HMC/main_VI_HMC_burgers.py:127-137).  The subsets come from Python's global ``random`` exactly as in the
+    reference (seed it for reproducibility); all chains of the call share them.  The iteration is composed on the host from the
+    exported building blocks (vihmc_momentum_philox, vihmc_logp_grad on the gathered problem, vihmc_leapfrog_update,
+    vihmc_mh_accept): a DeepONet evaluation is milliseconds of GPU work, so the Python loop only enqueues."""
+    import random
+
+    prep = prepare(spec)
+    sp = prep.spec
+    if sp.model_kind != MODEL_DEEPONET or sp.trunk_subsample is None:
+        raise ValueError("run_sampler_trunk_subsample needs a DeepONet spec with trunk_subsample set")
+    dev, d, P, psub = prep.device, sp.d, sp.P, int(sp.trunk_subsample)
+    q = _to_dev(q0.reshape(-1, d), dev).clone()
+    Cn = q.shape[0]
+    rows = num_samples - burn
+    if rows < 1:
+        raise RuntimeError("burn must be less than num_samples.")
+    samples = torch.empty((rows, Cn, d), dtype=torch.float32, device=dev)
+    samples[0].copy_(q)
+    acc = torch.empty((num_samples, Cn), dtype=torch.uint8, device=dev)
+    ham = torch.empty((num_samples, Cn, 2), dtype=torch.float32, device=dev)
+    fb_burn, fb_post = q.clone(), q.clone()   # param_burn_prev / ret_params[-1] of hamiltorch
+    inj_p, inj_u = _to_dev(inject_momenta, dev), _to_dev(inject_uniforms, dev)
+
+    def closure():
+        return _TrunkSubset(prep, random.sample(range(P), psub))
+
+    row = 1
+    for n in range(num_samples):
+        p = inj_p[n].clone() if inj_p is not None else momentum_philox(seed, n, chain_offset, Cn, d, dev)
+        u = inj_u[n].contiguous() if inj_u is not None else uniform_philox(seed, n, chain_offset, Cn, dev)
+        q_prop = q.clone()
+        lp0, _ = closure().logp_grad(q_prop, need_grad=False)
+        ke0 = leapfrog_update(q_prop, p, p, 0.0, 0.0, 0.0, want_ke=True)
+        _, g = closure().logp_grad(q_prop)
+        leapfrog_update(q_prop, p, g, step_size, 0.5, 1.0)                 # p += eps/2 g ; q += eps p
+        for s_ in range(1, num_steps + 1):
+            _, g = closure().logp_grad(q_prop)
+            if s_ < num_steps:
+                leapfrog_update(q_prop, p, g, step_size, 1.0, 1.0)         # p += eps g ; q += eps p
+            else:
+                leapfrog_update(q_prop, p, g, step_size, 1.0, 0.0)         # p += eps g
+        ke1 = leapfrog_update(q_prop, p, g, step_size, -0.5, 0.0, want_ke=True)   # p -= eps/2 g
+        lp1, _ = closure().logp_grad(q_prop, need_grad=False)
+        H0, H1 = ke0 - lp0, ke1 - lp1
+        ham[n, :, 0].copy_(H0)
+        ham[n, :, 1].copy_(H1)
+        if n > burn:
+            mh_accept(H0, H1, u, q_prop, q, fb_post, stored=samples[row], accepted=acc[n])
+            row += 1
+        else:
+            mh_accept(H0, H1, u, q_prop, q, fb_burn, accepted=acc[n])
+    res = SampleResult(samples, acc, ham, None, None, grad_evals_per_chain=num_samples * (num_steps + 1), gpu_launches=-1)
+    if to_host:
+        torch.cuda.current_stream(dev).synchronize()
+        res = SampleResult(samples.cpu(), acc.cpu(), ham.cpu(), None, None, res.grad_evals_per_chain, -1)
+    return res
+
+
 def momentum_philox(seed: int, iteration: int, chain0: int, chains: int, d: int, device=None) -> torch.Tensor:
     dev = _require_cuda(device)
     p = torch.empty((chains, d), dtype=torch.float32, device=dev)

@@ -116,6 +116,18 @@ def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, 
             recovered = specs[i]
             specs[i] = engine.prepare(recovered)
             closure.verify_closure(fn, recovered, q0[0], prepared=specs[i])
+    if spec0.trunk_subsample is not None:
+        # cfg.sample_data: every closure call redraws its trunk points; composed on the host from the exported building blocks
+        if len(specs) != 1 or nuts:
+            raise NotImplementedError("trunk sub-sampling (cfg.sample_data) is implemented for plain HMC with one log-posterior")
+        res = engine.run_sampler_trunk_subsample(specs[0], q0, num_samples, num_steps_per_sample, float(step_size), burn=burn, seed=seed,
+                                                 chain_offset=chain_offset, inject_momenta=inject_momenta,
+                                                 inject_uniforms=inject_uniforms, to_host=True)
+        if verbose or debug:
+            print("Acceptance Rate {:.2f}".format(res.acceptance_rate))
+        if return_result:
+            return res
+        return list(res.samples[:, 0, :].unbind(0)) if single else res.samples
     res = engine.run_sampler(specs, q0, num_samples, num_steps_per_sample, float(step_size), burn=burn, integrator=integ,
                              adapt_step_size=nuts, desired_accept_rate=desired_accept_rate, seed=seed,
                              chain_offset=chain_offset, hamiltorch_fallback_rule=hamiltorch_fallback_rule,
@@ -177,8 +189,8 @@ def define_model_log_prob_hamiltorch(model, model_loss, x, y, params_flattened_l
 
 
 def define_model_log_prob_deeponet(model, model_loss, tr_data, tau_list, tau_out, predict=False, prior_scale=1.0,
-                                   device='cpu', *, mean_params=None, std_params=None, grad_ind=None, load_prior=False
-                                   ) -> LogProbSpec:
+                                   device='cpu', *, mean_params=None, std_params=None, grad_ind=None, load_prior=False,
+                                   sample_data=False, p=None) -> LogProbSpec:
     """Operator_network/VI_HMC/main_VI_HMC_burgers.py:27-180 and Operator_network/HMC/main_HMC_splitting.py:79-206.
 
     tr_data = (x1 [N,1,in_branch], x2 [1,P,2], y [N,P]) as util.get_burgers_data returns (util.py:461-473).
@@ -196,7 +208,8 @@ def define_model_log_prob_deeponet(model, model_loss, tr_data, tau_list, tau_out
                        prior_mu=prior_mu, prior_sigma=prior_sigma, prior_sigma_scalar=scal, prior_scale=float(prior_scale),
                        frozen=None if mean_params is None else mean_params.detach().float().cpu(),
                        sens_ind=None if mean_params is None else np.asarray(grad_ind, dtype=np.int64),
-                       vi_sigma=None if std_params is None else std_params.detach().float().cpu(), predict=predict)
+                       vi_sigma=None if std_params is None else std_params.detach().float().cpu(), predict=predict,
+                       trunk_subsample=int(p) if (sample_data and not predict) else None)   # cfg.sample_data / cfg.p, :127-137
 
 
 def define_split_model_log_prob(model, model_loss, train_loader, num_splits, tau_list, tau_out, predict=False,

@@ -154,6 +154,7 @@ class LogProbSpec:
     sens_ind: Optional[np.ndarray] = None          # sorted int64 [d] or None
     vi_sigma: Optional[torch.Tensor] = None        # [D] VI stds, only for the optional redraw hook
     predict: bool = False
+    trunk_subsample: Optional[int] = None          # DeepONet: cfg.p trunk points redrawn for every closure call (cfg.sample_data)
 
     @property
     def model_kind(self) -> int:
@@ -198,6 +199,11 @@ class LogProbSpec:
             if tuple(self.y.shape) != (self.N, int(self.x2.shape[0])):
                 raise ValueError("y must be [N, P]")
         loss_code(self.loss)
+        if self.trunk_subsample is not None:
+            if self.model_kind != MODEL_DEEPONET:
+                raise ValueError("trunk_subsample is a DeepONet option (cfg.sample_data)")
+            if not 1 <= int(self.trunk_subsample) <= self.P:
+                raise ValueError("Sample larger than population or is negative")   # random.sample's message
 
 
 def sliced_prior_sigma(d: int, tensor_numels: Sequence[int], prior_vars: Sequence[float]) -> np.ndarray:
