@@ -328,6 +328,14 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
                              "ncu (profiles/r01_ncu_details_mlp_small_sample_final2.csv, profiles/r01_summary.md): the binding unit is "
                              "the shared-memory pipe, l1tex lsu shared wavefronts 78 % of peak (303 per evaluation), 447 warp "
                              "instructions per evaluation, issue slots 29 % busy; DRAM 217 KB read / 0 written per 40-iteration launch"},
+        # the unit that actually binds this kernel (ncu): shared-memory wavefronts.  303 wavefronts per chain-grad-eval is a constant
+        # of the compiled kernel (profiles/r01_ncu_details_mlp_small_sample_final2.csv: l1tex__data_pipe_lsu_wavefronts_mem_shared
+        # 2.446e9 for 1024 chains x 40 iterations x 197 evaluations); the pipe delivers one wavefront per clock per SM
+        "roofline_binding_unit": {"bound": "shared-memory pipe (l1tex lsu wavefronts)", "unit": "Gwavefronts/s",
+                                  "achieved": 303.0 * (CHAINS_PER_GPU * steps * (L_STEPS + 1)) / (ms * 1e-3) / 1e9,
+                                  "peak": 148 * sm_max_mhz * 1e6 / 1e9,
+                                  "frac": 303.0 * (CHAINS_PER_GPU * steps * (L_STEPS + 1)) / (ms * 1e-3) / (148 * sm_max_mhz * 1e6),
+                                  "wavefronts_per_chain_grad_eval": 303.0},
         "cpu_baseline": cpu_baseline_leg() if (world == 1 and not skip_cpu) else None,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
                 "seconds": e2e_s},
