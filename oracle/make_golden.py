@@ -325,8 +325,75 @@ def deeponet_cases():
     print("wrote", out, os.path.getsize(out) // 1024, "KiB")
 
 
+def deeponet_fullsize_cases():
+    """BASELINE sizes: N = 1000 functions, P = 10201 trunk points, D = 172 401.  The REAL reference
+    closures -- VI split (Operator_network/VI_HMC/main_VI_HMC_burgers.py:27-180, d = 17 240), full HMC and the M = 2 split closures
+    (Operator_network/HMC/main_HMC_splitting.py:79-258) -- evaluated with torch.autograd.grad at two points each.  Inputs come from
+    vihmc.synth.burgers_like(seed=0) / deeponet_vi_artifacts(seed=1) and are NOT stored; stored: q, logp (fp64 of the fp32 result),
+    grad (fp32), and an fp64 twin (oracle/closures.py at float64) of the full and VI closures at the first point for error attribution."""
+    from oracle import closures as oc
+
+    arch = DeepONetArch()
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=1000, n_t=101, n_x=101, seed=0)
+    mu, sigma, ind = synth.deeponet_vi_artifacts(theta, frac=0.10, seed=1)
+    tr_data = (x1.unsqueeze(1), x2.unsqueeze(0), y)
+    flat = {}
+    m = ref_loader.load_deeponet_vi_hmc()
+    ms = ref_loader.load_deeponet_split_hmc()
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw64 = dict(width_branch=arch.width_branch, width_trunk=arch.width_trunk, in_branch=arch.in_branch, in_trunk=arch.in_trunk,
+                depth_branch=arch.depth_branch, depth_trunk=arch.depth_trunk, output_neurons=arch.output_neurons, act=arch.act,
+                impose_bc=arch.impose_bc, loss="NLL", tau_out=1.0, prior_var=0.1 ** 2, dtype=torch.float64)
+    # ---- VI-HMC closure ----
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg = _don_module_cfg(m, arch)
+        cfg.prior_file, cfg.prior_uid = tmp, "synthetic"
+        _write_artifacts(tmp, "synthetic", mu, sigma, ind)
+        net = m.DeepONet(arch.width_branch, arch.width_trunk, arch.in_branch, arch.in_trunk, arch.depth_branch, arch.depth_trunk,
+                         arch.act, arch.output_neurons)
+        closure = m.define_model_log_prob(net, "NLL", tr_data, [torch.tensor(cfg.prior_var)], 1.0, device="cpu")
+        rs = np.random.RandomState(17)
+        d = len(ind)
+        qs = (mu.numpy()[ind][None] + sigma.numpy()[ind][None] * rs.randn(2, d)).astype(np.float32)
+        lps, grads = zip(*[_grad(closure, torch.from_numpy(q)) for q in qs])
+        flat["vi/q"], flat["vi/logp"], flat["vi/grad"] = qs, np.array(lps, np.float64), np.stack(grads).astype(np.float32)
+        twin = oc.DeepONetLogProb(x1=tr_data[0], x2=tr_data[1], y=y, frozen=mu, sens_ind=ind, **kw64)
+        lp64, g64 = _grad(twin, torch.from_numpy(qs[0]).double())
+        flat["vi/logp_f64"], flat["vi/grad_f64"] = np.array([lp64], np.float64), g64.astype(np.float32)[None]
+        print("fullsize vi logp", lps, "fp64 twin", lp64)
+    # ---- full-HMC closure + the M = 2 split closures ----
+    cfgs = ms.cfg
+    cfgs.branch_depth, cfgs.trunk_depth, cfgs.activation = arch.depth_branch, arch.depth_trunk, arch.act
+    cfgs.sample_data, cfgs.load_prior, cfgs.dataset = False, False, "Burgers"
+    net = ms.DeepONet(arch.width_branch, arch.width_trunk, arch.in_branch, arch.in_trunk, arch.depth_branch, arch.depth_trunk,
+                      arch.act, arch.output_neurons)
+    tau_list = [torch.tensor(cfgs.prior_var)]
+    full = ms.define_model_log_prob(net, "NLL", tr_data, tau_list, 1.0, device="cpu")
+    split_data = [(tr_data[0][i * 500:(i + 1) * 500], tr_data[1], tr_data[2][i * 500:(i + 1) * 500]) for i in range(2)]
+    splits = ms.define_split_model_log_prob(net, "NLL", split_data, 2, tau_list, 1.0, device="cpu", verbose=False)
+    rs = np.random.RandomState(18)
+    qs = (theta.numpy()[None] + 0.002 * rs.randn(2, arch.num_params)).astype(np.float32)
+    lps, grads = zip(*[_grad(full, torch.from_numpy(q)) for q in qs])
+    flat["full/q"], flat["full/logp"], flat["full/grad"] = qs, np.array(lps, np.float64), np.stack(grads).astype(np.float32)
+    for si, sc in enumerate(splits):
+        lp, g = _grad(sc, torch.from_numpy(qs[0]))
+        flat[f"split{si}/logp"], flat[f"split{si}/grad"] = np.array([lp], np.float64), g.astype(np.float32)[None]
+    twin = oc.DeepONetLogProb(x1=tr_data[0], x2=tr_data[1], y=y, **kw64)
+    lp64, g64 = _grad(twin, torch.from_numpy(qs[0]).double())
+    flat["full/logp_f64"], flat["full/grad_f64"] = np.array([lp64], np.float64), g64.astype(np.float32)[None]
+    flat["meta"] = np.array([1000, 101, 101, 100], np.int64)
+    print("fullsize full logp", lps, "fp64 twin", lp64, "splits", float(flat["split0/logp"][0]), float(flat["split1/logp"][0]))
+    out = os.path.join(GOLDEN, "deeponet_fullsize_logp_grad.npz")
+    np.savez_compressed(out, **flat)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1:   # python oracle/make_golden.py deeponet_fullsize_cases  (one generator only)
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     bnn_data_file()
     bnn_vi_hmc_cases()
     deeponet_cases()
@@ -334,3 +401,4 @@ if __name__ == "__main__":
     deeponet_sensitivity_cases()
     bnn_vi_training_cases()
     deeponet_vi_training_case()
+    deeponet_fullsize_cases()

@@ -20,8 +20,12 @@ RTOL = 1e-5
 
 
 def _assert_grad_close(got, ref, rtol=RTOL):
+    """component-wise relative to the largest component AND norm-wise over the whole vector (a systematic error in the
+    small components cannot hide behind max|g|)."""
     scale = np.abs(ref).max()
     np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * scale)
+    got64, ref64 = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert np.linalg.norm(got64 - ref64) <= rtol * np.linalg.norm(ref64)
 
 
 @pytest.mark.parametrize("name", cases.BNN_CASES)
@@ -216,21 +220,49 @@ def test_persistent_kernel_matches_general_sampler():
 
 
 def test_dual_averaging_matches_oracle():
+    """Sampler.HMC_NUTS = fixed-L HMC with dual averaging while n < burn (hamiltorch adaptation(): gamma .05, t0 10, kappa .75,
+    mu = log(10 eps0)).  Two things make the recursion itself the thing compared:
+    * the Metropolis decisions are FORCED by the injected uniforms (u = 1e-30: log u = -69, accept; u = 2: log u > 0 >= rho,
+      reject), so engine and oracle walk the same chain whatever the rounding;
+    * the likelihood variance is 25 instead of 0.0025, so |H| ~ 100 and its fp32 resolution (1e-5) no longer perturbs
+      alpha = min(1, exp(H0 - H1)) -- at the bench problem's |H| ~ 1e5 the resolution 0.008 alone moves eps by a few per cent.
+    Asserted for EVERY k <= burn: the step size after k adaptation steps (a run of k+1 iterations with burn = k ends with
+    eps = eps_bar_k), and in the longest run H0 / H1 / the energy error of every iteration (iteration n is integrated with the adapted
+    eps_n, so dH pins eps_n itself); alpha takes values 0.058 ... 1 along this run (oracle dH: 2e-4, 2.85, 9e-3, -0.05, -0.30, 0.30 ...)."""
     g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
-    case = cases.bnn_case(g, "d40_nll")
+    case = dict(cases.bnn_case(g, "d40_nll"))
+    case["tau_out"] = 25.0
     spec = cases.bnn_spec(case)
-    d, S, L, burn = case["d"], 12, 6, 8
+    d, S, L, burn, eps0 = case["d"], 9, 6, 7, 0.05
     rs = np.random.RandomState(21)
     q0 = torch.from_numpy(case["q"][0])[None]
-    p = torch.from_numpy(rs.randn(S, 1, d).astype(np.float32))
-    u = torch.from_numpy(rs.uniform(0.05, 1, size=(S, 1)).astype(np.float32))
-    res = engine.run_sampler([spec], q0, S, L, 1e-4, burn=burn, adapt_step_size=True, inject_momenta=p, inject_uniforms=u)
+    p = torch.from_numpy(rs.randn(16, 1, d).astype(np.float32))[:S]
+    u = torch.full((S, 1), 1e-30)
+    u[[2, 5, 6]] = 2.0
+    forced = [n not in (2, 5, 6) for n in range(S)]
     closure = cases.bnn_oracle(case, dtype=torch.float64)
-    _, tr = _run_oracle_chain(closure, q0[0].double(), S, L, 1e-4, burn, p[:, 0].double(), u[:, 0], sampler=hr.Sampler.HMC_NUTS)
-    if tr["accept"] == [bool(a) for a in res.accepted[:, 0].numpy()]:
-        assert abs(float(res.step_sizes[0]) - tr["final_step_size"]) <= 2e-3 * tr["final_step_size"]
-    # with or without identical decisions the first adapted step sizes follow the same recursion
-    assert float(res.step_sizes[0]) > 0
+    eps_bars = []
+    for k in range(1, burn + 1):
+        res = engine.run_sampler([spec], q0, k + 1, L, eps0, burn=k, adapt_step_size=True, inject_momenta=p[:k + 1],
+                                 inject_uniforms=u[:k + 1])
+        _, tr = _run_oracle_chain(closure, q0[0].double(), k + 1, L, eps0, k, p[:k + 1, 0].double(), u[:k + 1, 0],
+                                  sampler=hr.Sampler.HMC_NUTS)
+        assert tr["accept"] == forced[:k + 1] == [bool(a) for a in res.accepted[:, 0].numpy()]
+        assert abs(float(res.step_sizes[0]) - tr["final_step_size"]) <= 3e-3 * tr["final_step_size"], (k, float(res.step_sizes[0]),
+                                                                                                         tr["final_step_size"])
+        eps_bars.append(tr["final_step_size"])
+    assert max(eps_bars) / min(eps_bars) > 1.5
+    res = engine.run_sampler([spec], q0, S, L, eps0, burn=burn, adapt_step_size=True, inject_momenta=p, inject_uniforms=u)
+    out, tr = _run_oracle_chain(closure, q0[0].double(), S, L, eps0, burn, p[:, 0].double(), u[:, 0], sampler=hr.Sampler.HMC_NUTS)
+    assert tr["accept"] == forced == [bool(a) for a in res.accepted[:, 0].numpy()]
+    eps_trace = np.array(tr["step_size"])
+    assert eps_trace.max() / eps_trace.min() > 10.0          # the adaptation really moves the step size in this run
+    np.testing.assert_allclose(res.hamiltonians[:, 0, 0].numpy(), tr["H0"], rtol=2e-5)
+    np.testing.assert_allclose(res.hamiltonians[:, 0, 1].numpy(), tr["H1"], rtol=5e-4)
+    dH = (res.hamiltonians[:, 0, 1] - res.hamiltonians[:, 0, 0]).numpy().astype(np.float64)
+    dH_ref = np.array(tr["H1"]) - np.array(tr["H0"])
+    np.testing.assert_allclose(dH, dH_ref, rtol=2e-2, atol=5e-3)
+    np.testing.assert_allclose(res.samples[:, 0].numpy(), out.numpy(), rtol=1e-2, atol=1e-2)   # fp32 vs fp64 oracle: 2.6e-3
 
 
 def test_predict_matches_oracle_forward():

@@ -98,3 +98,85 @@ def test_prior_scale_is_linear(cfg3):
     prior = 2.0 * (vals[1.0] - vals[2.0])
     loglik = vals[1.0] - prior
     assert abs((loglik + prior / 4.0) - vals[4.0]) <= 2e-6 * abs(vals[4.0]) + 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE-size parity against the REAL reference closures (golden vectors: oracle/make_golden.py::deeponet_fullsize_cases)
+# ------------------------------------------------------------------------------------------------------------------
+FULLSIZE_RTOL = 1e-5     # BASELINE.json north_star: log-posterior and gradient within rtol 1e-5 in fp32
+
+
+def _tensor_slices(arch):
+    """(name, slice) of every parameter tensor in the flat DeepONet layout (b | branch W,b ... | trunk W,b ...)."""
+    out, off = [("b", slice(0, 1))], 1
+    for which in ("branch", "trunk"):
+        for li, (o, i) in enumerate(arch.stack_dims(which)):
+            for nm, n in (("W", o * i), ("b", o)):
+                out.append((f"{which}{li}.{nm}", slice(off, off + n)))
+                off += n
+    assert off == arch.num_params
+    return out
+
+
+def _assert_fullsize_close(got, ref, f64=None, slices=None, what=""):
+    """max-relative (to the largest component), norm-relative over the whole vector and, for full vectors, norm-relative per
+    parameter tensor -- so that a systematic error in a tensor of small gradients (first layers) cannot hide behind max|g|."""
+    got, ref = got.astype(np.float64), ref.astype(np.float64)
+    err = np.abs(got - ref)
+    rel_max = err.max() / np.abs(ref).max()
+    rel_norm = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    msg = f"{what}: max-rel {rel_max:.2e} norm-rel {rel_norm:.2e}"
+    if f64 is not None:   # error attribution: how far the reference's own fp32 sits from fp64, and how far we do
+        f64 = f64.astype(np.float64)
+        msg += (f" | vs fp64 twin: ours {np.linalg.norm(got - f64) / np.linalg.norm(f64):.2e}, "
+                f"reference fp32 {np.linalg.norm(ref - f64) / np.linalg.norm(f64):.2e}, "
+                f"mean signed rel err ours {np.mean((got - f64) / np.abs(f64).max()):.2e}")
+    print(msg)
+    assert rel_max <= FULLSIZE_RTOL, msg
+    assert rel_norm <= FULLSIZE_RTOL, msg
+    if slices is not None:
+        for name, sl in slices:
+            n = np.linalg.norm(ref[sl])
+            if n > 0:
+                r = np.linalg.norm(got[sl] - ref[sl]) / n
+                assert r <= FULLSIZE_RTOL, f"{what} tensor {name}: norm-rel {r:.2e}"
+
+
+@pytest.fixture(scope="module")
+def fullsize_golden():
+    import cases
+    return cases.load_golden("deeponet_fullsize_logp_grad.npz")
+
+
+def test_cfg3_full_size_closure_matches_reference_golden(cfg3, fullsize_golden):
+    """a4 at BASELINE size: full-HMC closure (main_HMC_splitting.py:134-204) and its M = 2 split closures (:209-258) at
+    N = 1000, P = 10201, D = 172 401 against values produced by the reference's own code."""
+    arch, x1, x2, y, theta = cfg3
+    g = fullsize_golden
+    kw = dict(arch=arch, x2=x2, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
+    q = torch.from_numpy(g["full/q"])
+    logp, grad = engine.logp_grad(LogProbSpec(x=x1, y=y, **kw), q)
+    np.testing.assert_allclose(logp.double().cpu().numpy(), g["full/logp"], rtol=FULLSIZE_RTOL)
+    sl = _tensor_slices(arch)
+    for i in range(q.shape[0]):
+        _assert_fullsize_close(grad[i].cpu().numpy(), g["full/grad"][i], g["full/grad_f64"][0] if i == 0 else None, sl, f"full q{i}")
+    print("full logp ours", logp.double().cpu().numpy(), "reference", g["full/logp"], "fp64 twin", g["full/logp_f64"])
+    for si in range(2):
+        sp = LogProbSpec(x=x1[si * 500:(si + 1) * 500], y=y[si * 500:(si + 1) * 500], prior_scale=2.0, **kw)
+        lp, gr = engine.logp_grad(sp, q[:1])
+        np.testing.assert_allclose(lp.double().cpu().numpy(), g[f"split{si}/logp"], rtol=FULLSIZE_RTOL)
+        _assert_fullsize_close(gr[0].cpu().numpy(), g[f"split{si}/grad"][0], None, sl, f"split{si}")
+
+
+def test_cfg4_full_size_vi_closure_matches_reference_golden(cfg3, fullsize_golden):
+    """a4 at BASELINE size: VI-HMC closure (main_VI_HMC_burgers.py:86-178), d = 17 240 of D = 172 401."""
+    arch, x1, x2, y, theta = cfg3
+    g = fullsize_golden
+    mu, sigma, ind = synth.deeponet_vi_artifacts(theta, 0.10, seed=1)
+    spec = LogProbSpec(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1, frozen=mu, sens_ind=ind)
+    q = torch.from_numpy(g["vi/q"])
+    logp, grad = engine.logp_grad(spec, q)
+    np.testing.assert_allclose(logp.double().cpu().numpy(), g["vi/logp"], rtol=FULLSIZE_RTOL)
+    for i in range(q.shape[0]):
+        _assert_fullsize_close(grad[i].cpu().numpy(), g["vi/grad"][i], g["vi/grad_f64"][0] if i == 0 else None, None, f"vi q{i}")
+    print("vi logp ours", logp.double().cpu().numpy(), "reference", g["vi/logp"], "fp64 twin", g["vi/logp_f64"])

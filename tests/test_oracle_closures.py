@@ -1,11 +1,14 @@
 """CPU: pin the oracle restatement (oracle/closures.py) against golden vectors produced by the
 REAL reference closures (oracle/make_golden.py).  Tolerances: the restatement uses the same torch ops
 in the same order, so fp32 agreement is to a few ulp of the ~1e5-sized log-probability."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import cases
+from cases import GOLDEN
 from oracle import closures as oc
 
 
@@ -95,3 +98,18 @@ def test_reference_still_agrees_when_present():
         (gr,) = torch.autograd.grad(lp, q)
     assert abs(float(lp) - case["logp"][0]) <= 1e-6 * abs(case["logp"][0])
     np.testing.assert_allclose(gr.numpy(), case["grad"][0], rtol=1e-6, atol=1e-3)
+
+
+def test_fullsize_golden_is_self_consistent():
+    """BASELINE-size golden vectors (reference closures at N = 1000, P = 10201, D = 172 401): the M = 2 split closures add up to the
+    full closure (main_HMC_splitting.py:209-258), the VI gradient is finite, and the reference's fp32 results sit within 1e-5 of the
+    fp64 twin of the restatement -- which pins the restatement at this size without re-running it in the CPU suite."""
+    g = np.load(os.path.join(GOLDEN, "deeponet_fullsize_logp_grad.npz"))
+    full = g["full/grad"][0].astype(np.float64)
+    s = g["split0/grad"][0].astype(np.float64) + g["split1/grad"][0]
+    assert np.abs(full - s).max() <= 1e-6 * np.abs(full).max()
+    assert abs(g["split0/logp"][0] + g["split1/logp"][0] - g["full/logp"][0]) <= 1e-6 * abs(g["full/logp"][0])
+    for k in ("vi", "full"):
+        a, b = g[f"{k}/grad"][0].astype(np.float64), g[f"{k}/grad_f64"][0].astype(np.float64)
+        assert np.linalg.norm(a - b) <= 1e-5 * np.linalg.norm(b)
+        assert abs(g[f"{k}/logp"][0] - g[f"{k}/logp_f64"][0]) <= 1e-5 * abs(g[f"{k}/logp_f64"][0])
