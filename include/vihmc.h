@@ -302,6 +302,17 @@ VIHMC_API int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t 
                      void* stream);
 
 /*
+ * Test hook for the exact-accumulation forward products (csrc/xgemm.cuh): C[b][M,N] = A[b][M,K] B[b][N,K]^T, K <= 112,
+ * row-major fp32 operands with row strides lda / ldb.  Builds the three-piece bf16 operand images + row scales in
+ * `workspace` (vihmc_debug_xgemm_workspace_bytes) and multiplies them with tcgen05.mma.kind::f16; every accumulation inside
+ * the tensor core is exact by construction, so C differs from the exactly-rounded product only by the 2^-24 rounding of the
+ * operands and one fp32 rounding of the sum.  The tests pin that property against fp64.
+ */
+VIHMC_API size_t vihmc_debug_xgemm_workspace_bytes(int32_t M, int32_t N, int32_t batch);
+VIHMC_API int vihmc_debug_xgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int32_t M,
+                      int32_t N, int32_t K, int32_t batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Host-buffer convenience entry (everything is a HOST pointer, including those inside prob): allocates
  * device memory, copies in, runs vihmc_mlp_sample or vihmc_sample, copies samples/diagnostics out.
  */

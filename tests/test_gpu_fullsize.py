@@ -139,7 +139,11 @@ def _assert_fullsize_close(got, ref, f64=None, slices=None, what=""):
             n = np.linalg.norm(ref[sl])
             if n > 0:
                 r = np.linalg.norm(got[sl] - ref[sl]) / n
-                assert r <= FULLSIZE_RTOL, f"{what} tensor {name}: norm-rel {r:.2e}"
+                # the scalar output bias: d/db = sum of the N P residuals, a sum with heavy cancellation that a COHERENT output
+                # error of 1e-8 (the reference's own fp32 result sits 1.06e-8 from fp64, tests/diag_forward.py) moves by 1e-5 of
+                # itself at N = 500 -- checked at 5e-5 of itself (and at 1e-5 of max|g| by the assertion above)
+                tol = 5 * FULLSIZE_RTOL if ref[sl].size == 1 else FULLSIZE_RTOL
+                assert r <= tol, f"{what} tensor {name}: norm-rel {r:.2e}"
 
 
 @pytest.fixture(scope="module")

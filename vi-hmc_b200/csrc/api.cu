@@ -40,6 +40,9 @@ int dense_logp_grad(const vihmc_problem*, long long C, const float* q, float* lo
 int dense_predict(const vihmc_problem*, long long C, const float* q, float* out, void* ws, size_t ws_bytes, cudaStream_t);
 int dense_umma_probe(const float* a_img, const float* b_img, unsigned a_lbo, unsigned a_sbo, unsigned b_lbo, unsigned b_sbo,
                      unsigned a_type, unsigned b_type, unsigned idesc_extra, float* out, cudaStream_t);
+size_t dense_xgemm_workspace(int M, int N, int batch);
+int dense_xgemm_debug(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M, int N, int K,
+                      int batch, void* ws, size_t ws_bytes, cudaStream_t st);
 int dense_gemm(const float* A, long long a_bs, long long a_sm, long long a_sk, const float* B, long long b_bs, long long b_sk,
                long long b_sn, float* C, long long c_bs, long long ldc, int M, int N, int K, int batch, int use_tc, float* scratch,
                cudaStream_t);
@@ -530,6 +533,14 @@ int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t a_lbo, uin
   if (int rc = device_check()) return rc;
   return dense_umma_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, a_layout_type, b_layout_type, idesc_extra, out,
                           static_cast<cudaStream_t>(stream));
+}
+
+size_t vihmc_debug_xgemm_workspace_bytes(int32_t M, int32_t N, int32_t batch) { return dense_xgemm_workspace(M, N, batch); }
+
+int vihmc_debug_xgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                      int32_t batch, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = device_check()) return rc;
+  return dense_xgemm_debug(A, lda, B, ldb, C, ldc, M, N, K, batch, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 size_t vihmc_mlp_sensitivity_workspace_bytes(const vihmc_problem* prob) {

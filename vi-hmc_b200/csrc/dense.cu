@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "fused_stack.cuh"
+#include "xgemm.cuh"
+#include "fwd3.cuh"
 
 namespace vihmc {
 
@@ -401,6 +403,10 @@ struct DensePlan {
   long long img_floats;      // pre-split weight images of the fused kernels (0 when no stack is eligible)
   long long dzall_floats;    // fused trunk backward: dz of every layer below the top one + bias-gradient partials
   long long shared_floats;  // trunk features
+  // exact-accumulation forward (fwd3.cuh): weight blobs, operand images of Bout / Tout and their row scales
+  bool fwd3;
+  int m_tiles, p_tiles128;
+  long long wimg3_floats, ximg_a_floats, ximg_b_floats, xsc_floats;
 };
 
 // VIHMC_DENSE_NOFUSE=1 keeps every stack on the per-layer GEMMs (A/B baseline of the fused kernel)
@@ -483,6 +489,84 @@ static int stack_backward_fused(const Stack& s, const float* input, long long R,
   return VIHMC_OK;
 }
 
+// VIHMC_DENSE_FWD3=0 keeps the forward pass on the 3xTF32 kernels (A/B runs; that path carries the tensor core's
+// accumulate-truncation bias, see xgemm.cuh)
+static bool fwd3_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("VIHMC_DENSE_FWD3");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on && tensor_cores_enabled();
+}
+static bool fwd3_eligible(const Stack& s) {
+  if (s.n_layers < 2 || s.in_dim > xg::XK) return false;
+  for (int l = 0; l < s.n_layers; ++l)
+    if (s.dims[l] % 4 != 0 || s.dims[l] > fused::KPAD || !s.has_bias[l]) return false;
+  return true;
+}
+
+// forward of one stack through fused_forward3_kernel; out_img / out_scales (optional): operand image of the last layer's output
+static int stack_forward3(const Stack& s, const float* input, long long R, const float* Wf, long long Dp, float* const* acts, int act,
+                          int Cb, unsigned char* wimg, unsigned char* out_img, float* out_scales, cudaStream_t st) {
+  xg::Img3Table t{};
+  const int l0 = s.in_dim > xg::MAX_IN0 ? 0 : 1;
+  t.n = s.n_layers - l0;
+  for (int l = l0; l < s.n_layers; ++l) t.L[l - l0] = xg::Img3Layer{s.w_off[l], s.b_off[l], s.dims[l], s.in_of(l), s.ldw[l], 1};
+  xg::weight_image3_kernel<<<dim3(t.n, Cb), 256, 0, st>>>(Wf, Dp, t, wimg);
+  VIHMC_LAUNCH_OK("weight_image3_kernel");
+  xg::Fwd3Args a{};
+  a.input = input; a.in_dim = s.in_dim; a.Wf = Wf; a.Dp = Dp; a.w0_off = s.w_off[0]; a.b0_off = s.b_off[0]; a.ldw0 = s.ldw[0];
+  for (int l = 0; l < s.n_layers; ++l) { a.dims[l] = s.dims[l]; a.acts[l] = acts[l]; }
+  a.n_layers = s.n_layers; a.wimg = wimg; a.R = R; a.out_img = out_img; a.out_scales = out_scales;
+  const dim3 grid((unsigned)((R + 127) / 128), Cb);
+  auto launch = [&](auto kernel) -> int {
+    VIHMC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xg::F3_SMEM));
+    kernel<<<grid, xg::F3_THREADS, xg::F3_SMEM, st>>>(a);
+    return VIHMC_OK;
+  };
+  if (act == VIHMC_ACT_TANH) { if (int rc = launch(xg::fused_forward3_kernel<VIHMC_ACT_TANH>)) return rc; }
+  else { if (int rc = launch(xg::fused_forward3_kernel<VIHMC_ACT_RELU>)) return rc; }
+  VIHMC_LAUNCH_OK("fused_forward3_kernel");
+  return VIHMC_OK;
+}
+
+// head product + Gaussian residual (likelihood mode) or plain outputs (predict mode) through head3_kernel
+static int launch_head3(const DensePlan& pl, int Cb, const unsigned char* a_img, const float* a_sc, const unsigned char* b_img,
+                        const float* b_sc, const float* bias, long long bias_bs, const float* Y, long long ldy, float* G, long long g_bs,
+                        long long ldg, const Likelihood& lik, float* part_ll, float* part_g, int* parts_out, cudaStream_t st) {
+  xg::Head3Args a{};
+  a.a_img = a_img; a.a_sc = a_sc; a.b_img = b_img; a.b_sc = b_sc;
+  a.M = (int)pl.N; a.P = (int)pl.P; a.K = pl.K;
+  a.bias = bias; a.bias_bs = bias_bs; a.Y = Y; a.ldy = ldy; a.G = G; a.g_bs = g_bs; a.ldg = ldg;
+  a.ll_const = lik.ll_const; a.half_prec = lik.half_prec; a.prec = lik.prec;
+  a.part_ll = part_ll; a.part_g = part_g;
+  a.Cb = Cb; a.m_tiles = pl.m_tiles; a.p_tiles128 = pl.p_tiles128;
+  a.p_tiles = (int)((pl.P + xg::H3_BN - 1) / xg::H3_BN);
+  // trunk-point chunks: enough work items to balance the persistent CTAs, at least four tiles per item, and no more
+  // partial-sum slots per chain than the workspace holds (head_tiles)
+  const int sms = tc_num_sms();
+  long long want = (6LL * sms + (long long)Cb * a.m_tiles - 1) / ((long long)Cb * a.m_tiles);
+  long long cap = a.p_tiles / 4 > 1 ? a.p_tiles / 4 : 1;
+  if (cap > pl.head_tiles / a.m_tiles) cap = pl.head_tiles / a.m_tiles;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  a.tiles_per_chunk = (int)((a.p_tiles + want - 1) / want);
+  a.p_chunks = (a.p_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  a.parts = a.m_tiles * a.p_chunks;
+  a.n_items = (long long)Cb * a.parts;
+  if (parts_out != nullptr) *parts_out = a.parts;
+  const unsigned grid = (unsigned)(a.n_items < sms ? a.n_items : sms);
+  if (Y == nullptr) {
+    VIHMC_CUDA_OK(cudaFuncSetAttribute(xg::head3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xg::H3_SMEM));
+    xg::head3_kernel<true><<<grid, xg::H3_THREADS, xg::H3_SMEM, st>>>(a);
+  } else {
+    VIHMC_CUDA_OK(cudaFuncSetAttribute(xg::head3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xg::H3_SMEM));
+    xg::head3_kernel<false><<<grid, xg::H3_THREADS, xg::H3_SMEM, st>>>(a);
+  }
+  VIHMC_LAUNCH_OK("head3_kernel");
+  return VIHMC_OK;
+}
+
 static int make_plan(const vihmc_problem* p, DensePlan& pl) {
   pl.deeponet = p->model_kind == VIHMC_MODEL_DEEPONET;
   pl.N = p->N;
@@ -530,9 +614,10 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long f = splitk_scratch_floats(pl.b.dims[l], pl.b.in_of(l), (int)pl.P, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
   }
-  if (pl.deeponet) {   // dBout = G Tout reduces over the P trunk points
-    const long long f = splitk_scratch_floats((int)pl.N, pl.K, (int)pl.P, 1);
+  if (pl.deeponet) {   // dBout = G Tout reduces over the P trunk points, dTout = G^T Bout over the N functions
+    const long long f = splitk_scratch_floats((int)pl.N, pl.K, (int)pl.P, 1), f2 = splitk_scratch_floats((int)pl.P, pl.K, (int)pl.N, 1);
     pl.scratch_per_chain = f > pl.scratch_per_chain ? f : pl.scratch_per_chain;
+    pl.scratch_per_chain = f2 > pl.scratch_per_chain ? f2 : pl.scratch_per_chain;
   }
   // fused kernels (DeepONet stacks): weight images (the two stacks use the buffer one after the other), dz of every layer
   pl.fuse_a = pl.deeponet && fused_eligible(pl.a);
@@ -548,7 +633,18 @@ static int make_plan(const vihmc_problem* p, DensePlan& pl) {
     const long long wa = pl.a.max_width();
     pl.dzall_floats += (long long)(pl.a.n_layers - 1) * (pl.N * wa + 64) + ((pl.N + 127) / 128 + 16) * wa + 64;
   }
-  pl.per_chain_floats = pl.dzall_floats + pl.img_floats + pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
+  pl.fwd3 = pl.deeponet && fwd3_enabled() && fwd3_eligible(pl.a) && fwd3_eligible(pl.b) && pl.K <= xg::XK;
+  pl.m_tiles = (int)((pl.N + 127) / 128);
+  pl.p_tiles128 = (int)((pl.P + 127) / 128);
+  pl.wimg3_floats = pl.ximg_a_floats = pl.ximg_b_floats = pl.xsc_floats = 0;
+  if (pl.fwd3) {
+    const int n_blobs = pl.a.n_layers > pl.b.n_layers ? pl.a.n_layers : pl.b.n_layers;
+    pl.wimg3_floats = (long long)n_blobs * (xg::XIMG_B / 4) + 64;
+    pl.ximg_a_floats = (long long)pl.m_tiles * (xg::XTILE / 4) + 64;
+    pl.ximg_b_floats = (long long)pl.p_tiles128 * (xg::XTILE / 4) + 64;
+    pl.xsc_floats = ((long long)pl.m_tiles + pl.p_tiles128) * 128 + 128;
+  }
+  pl.per_chain_floats = pl.wimg3_floats + pl.ximg_a_floats + pl.ximg_b_floats + pl.xsc_floats + pl.dzall_floats + pl.img_floats + pl.scratch_per_chain + 2 * pl.Dp + pl.act_a_floats + pl.act_b_floats + G + 2 * pl.R * wmax + 2 * tiles + 8 + 64 * 40 + pl.P + (p->d + 8191) / 8192;
   // shared by every chain: pad map, trunk features, padded copy of the targets
   pl.shared_floats = pl.D + 64 + (pl.deeponet ? pl.P * 5 + 64 + pl.N * pl.Pp + 64 : 0);
   return VIHMC_OK;
@@ -728,6 +824,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
   SharedBufs sb;
   if (int rc = prepare_shared(p, pl, ws, predict_out == nullptr, st, sb)) return rc;
   const float* trunk_in = sb.trunk_in;
+  if (pl.fwd3 && (reinterpret_cast<uintptr_t>(sb.y_pad) & 15u) != 0) return fail(VIHMC_ERR_INVALID, "targets must be 16-byte aligned");
 
   for (long long c0 = 0; c0 < C; c0 += cb_max) {
     const int Cb = (int)((C - c0) < cb_max ? (C - c0) : cb_max);
@@ -765,15 +862,27 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
       dzs_a[pl.a.n_layers - 1] = dz0;
       bias_part_a = bb.take((long long)Cb * (((N + 127) / 128 + 16) * wa));
     }
+    unsigned char *wimg3 = nullptr, *ximg_a = nullptr, *ximg_b = nullptr;
+    float *xsc_a = nullptr, *xsc_b = nullptr;
+    if (pl.fwd3) {
+      wimg3 = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.wimg3_floats));
+      ximg_a = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.ximg_a_floats));
+      ximg_b = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.ximg_b_floats));
+      xsc_a = bb.take((long long)Cb * pl.m_tiles * 128);
+      xsc_b = bb.take((long long)Cb * pl.p_tiles128 * 128);
+    }
     const float* qb = q + c0 * d;
 
     if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st)) return rc;
-    if (pl.fuse_a) {
+    if (pl.fwd3) {
+      if (int rc = stack_forward3(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, wimg3, ximg_a, xsc_a, st)) return rc;
+      if (int rc = stack_forward3(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, Cb, wimg3, ximg_b, xsc_b, st)) return rc;
+    } else if (pl.fuse_a) {
       if (int rc = stack_forward_fused(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, img, st)) return rc;
     } else {
       if (int rc = stack_forward(pl.a, p->x, N, Wf, Dp, acts_a, p->act, false, Cb, st)) return rc;
     }
-    if (pl.deeponet) {
+    if (pl.deeponet && !pl.fwd3) {
       if (pl.fuse_b) {
         if (int rc = stack_forward_fused(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, Cb, img, st)) return rc;
       } else {
@@ -796,10 +905,17 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
       g.aux = sb.y_pad; g.aux_bs = 0; g.ld_aux = Pp;
       g.ll_const = lik.ll_const; g.half_prec = lik.half_prec; g.prec = lik.prec;
       g.part_ll = part_ll; g.part_g = part_g;
-      if (int rc = launch_gemm<EPI_HEAD>(g, Cb, st)) return rc;
-      reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, tiles, Cb, loglik, 1);
+      long long parts = tiles;
+      if (pl.fwd3) {
+        int np = 0;
+        if (int rc = launch_head3(pl, Cb, ximg_a, xsc_a, ximg_b, xsc_b, Wf, Dp, sb.y_pad, Pp, G, N * Pp, Pp, lik, part_ll, part_g, &np, st)) return rc;
+        parts = np;
+      } else {
+        if (int rc = launch_gemm<EPI_HEAD>(g, Cb, st)) return rc;
+      }
+      reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_ll, parts, Cb, loglik, 1);
       if (grad != nullptr) {
-        reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_g, tiles, Cb, dWf, Dp);  // d/d b0 = sum G
+        reduce_partials_kernel<<<(Cb + 3) / 4, 128, 0, st>>>(part_g, parts, Cb, dWf, Dp);  // d/d b0 = sum G
         // dBout[n,k] = sum_p G[n,p] Tout[p,k]
         GemmArgs h{};
         h.A = G; h.a_bs = N * Pp; h.a_sm = Pp; h.a_sk = 1;
@@ -816,7 +932,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
         t.A = G; t.a_bs = N * Pp; t.a_sm = 1; t.a_sk = Pp;
         t.B = Bout; t.b_bs = N * K; t.b_sk = K; t.b_sn = 1;
         t.C = dz0; t.c_bs = P * K; t.ldc = K; t.M = (int)P; t.N = K; t.K = (int)N;
-        if (int rc = launch_gemm<EPI_STORE>(t, Cb, st)) return rc;
+        if (int rc = launch_gemm<EPI_STORE>(t, Cb, st, scratch)) return rc;
         if (bias_part_b != nullptr) {
           if (int rc = stack_backward_fused(pl.b, trunk_in, P, Wf, dWf, Dp, acts_b, dzs_b, p->act, Cb, img, bias_part_b, scratch, st)) return rc;
         } else {
@@ -869,6 +985,31 @@ int dense_umma_probe(const float* a_img, const float* b_img, unsigned a_lbo, uns
   return VIHMC_OK;
 }
 
+// vihmc_debug_xgemm (include/vihmc.h): C[b] = A[b] B[b]^T through the exact-accumulation operand images (xgemm.cuh)
+size_t dense_xgemm_workspace(int M, int N, int batch) {
+  const long long mt = (M + 127) / 128, nt = (N + 127) / 128;
+  return (size_t)((mt + nt) * batch * (long long)xg::XTILE + ((long long)M + N) * batch * 4 + 1024);
+}
+int dense_xgemm_debug(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M, int N, int K,
+                      int batch, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (A == nullptr || B == nullptr || C == nullptr || ws == nullptr) return fail(VIHMC_ERR_INVALID, "xgemm: null pointer");
+  if (K < 1 || K > xg::XK) return fail(VIHMC_ERR_UNSUPPORTED, "xgemm: K must be in [1, %d]", xg::XK);
+  if (ws_bytes < dense_xgemm_workspace(M, N, batch)) return fail(VIHMC_ERR_WORKSPACE, "xgemm: workspace too small");
+  const int mt = (M + 127) / 128, nt = (N + 127) / 128;
+  unsigned char* a_img = static_cast<unsigned char*>(ws);
+  unsigned char* b_img = a_img + (size_t)mt * batch * xg::XTILE;
+  float* a_sc = reinterpret_cast<float*>(b_img + (size_t)nt * batch * xg::XTILE);
+  float* b_sc = a_sc + (size_t)M * batch;
+  xg::image3_kernel<<<dim3(mt, batch), 256, 0, st>>>(A, (long long)M * lda, lda, M, K, a_img, a_sc, M);
+  VIHMC_LAUNCH_OK("image3_kernel");
+  xg::image3_kernel<<<dim3(nt, batch), 256, 0, st>>>(B, (long long)N * ldb, ldb, N, K, b_img, b_sc, N);
+  VIHMC_LAUNCH_OK("image3_kernel");
+  VIHMC_CUDA_OK(cudaFuncSetAttribute(xg::xgemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xg::XT_SMEM));
+  xg::xgemm_test_kernel<<<dim3(nt, mt, batch), 256, xg::XT_SMEM, st>>>(a_img, a_sc, b_img, b_sc, M, N, K, C, ldc);
+  VIHMC_LAUNCH_OK("xgemm_test_kernel");
+  return VIHMC_OK;
+}
+
 int dense_logp_grad(const vihmc_problem* p, long long C, const float* q, float* logp, float* grad, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
   return dense_run(p, C, q, logp, grad, nullptr, ws, ws_bytes, st);
@@ -900,6 +1041,19 @@ int dense_predict(const vihmc_problem* p, long long C, const float* q, float* ou
     float* part = bb.take(2LL * Cb * pl.head_tiles);
     float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
     if (int rc = scatter_padded(p, pl, sb.pad_map, q + c0 * d, Wf, Cb, st)) return rc;
+    if (pl.fwd3) {   // exact-accumulation forward: stacks, then the head kernel in predict mode writes out[c, n, p] directly
+      unsigned char* wimg3 = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.wimg3_floats));
+      unsigned char* ximg_a = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.ximg_a_floats));
+      unsigned char* ximg_b = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.ximg_b_floats));
+      float* xsc_a = bb.take((long long)Cb * pl.m_tiles * 128);
+      float* xsc_b = bb.take((long long)Cb * pl.p_tiles128 * 128);
+      if (int rc = stack_forward3(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, wimg3, ximg_a, xsc_a, st)) return rc;
+      if (int rc = stack_forward3(pl.b, sb.trunk_in, P, Wf, Dp, acts_b, p->act, Cb, wimg3, ximg_b, xsc_b, st)) return rc;
+      Likelihood none{};
+      if (int rc = launch_head3(pl, Cb, ximg_a, xsc_a, ximg_b, xsc_b, Wf, Dp, nullptr, 0, out + c0 * N * P, N * P, P, none, part,
+                                part + (long long)Cb * pl.head_tiles, nullptr, st)) return rc;
+      continue;
+    }
     if (pl.fuse_a) {
       if (int rc = stack_forward_fused(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, img, st)) return rc;
     } else {

@@ -824,8 +824,11 @@ __global__ void rowsum_finish_kernel(const float* __restrict__ part, int splits,
   }
 }
 
-constexpr int kSplitKChunk = 1024;      // K slice per CTA once K exceeds kSplitKThreshold
-constexpr int kSplitKThreshold = 2048;
+// The fp32 accumulate of tcgen05.mma truncates toward zero: a chain of k accumulations shrinks the sum by ~k/2 ulp.  At BASELINE
+// size (K = 10201) 1152-deep slices left 1.3e-5 relative error on the trunk's weight gradients (tests/diag_fullsize.py); with
+// 256-deep slices (32 chained accumulations) summed by round-to-nearest adds it is below 4e-6.
+constexpr int kSplitKChunk = 256;       // K slice per CTA once K exceeds kSplitKThreshold
+constexpr int kSplitKThreshold = 512;
 
 constexpr int kFillSplitMinK = 512;     // medium reductions are split only to put more CTAs on the GPU (few chains)
 constexpr int kFillSplitMax = 8;
