@@ -308,6 +308,9 @@ VIHMC_API int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t 
  * the tensor core is exact by construction, so C differs from the exactly-rounded product only by the 2^-24 rounding of the
  * operands and one fp32 rounding of the sum.  The tests pin that property against fp64.
  */
+/* Test hook: y[i] = tanh(x[i]) by one of the dense path's implementations (0: MUFU ex2/rcp form of the 3xTF32 kernels, 1: CUDA
+ * tanhf, 2: the unbiased Cody-Waite / Taylor form of the exact forward pass); n even. */
+VIHMC_API int vihmc_debug_tanh(int32_t kind, const float* x, float* y, int64_t n, void* stream);
 VIHMC_API size_t vihmc_debug_xgemm_workspace_bytes(int32_t M, int32_t N, int32_t batch);
 VIHMC_API int vihmc_debug_xgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int32_t M,
                       int32_t N, int32_t K, int32_t batch, void* workspace, size_t workspace_bytes, void* stream);

@@ -40,6 +40,7 @@ int dense_logp_grad(const vihmc_problem*, long long C, const float* q, float* lo
 int dense_predict(const vihmc_problem*, long long C, const float* q, float* out, void* ws, size_t ws_bytes, cudaStream_t);
 int dense_umma_probe(const float* a_img, const float* b_img, unsigned a_lbo, unsigned a_sbo, unsigned b_lbo, unsigned b_sbo,
                      unsigned a_type, unsigned b_type, unsigned idesc_extra, float* out, cudaStream_t);
+int dense_debug_tanh(int kind, const float* x, float* y, long long n, cudaStream_t st);
 size_t dense_xgemm_workspace(int M, int N, int batch);
 int dense_xgemm_debug(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M, int N, int K,
                       int batch, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -533,6 +534,11 @@ int vihmc_debug_umma(const float* a_img, const float* b_img, uint32_t a_lbo, uin
   if (int rc = device_check()) return rc;
   return dense_umma_probe(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, a_layout_type, b_layout_type, idesc_extra, out,
                           static_cast<cudaStream_t>(stream));
+}
+
+int vihmc_debug_tanh(int32_t kind, const float* x, float* y, int64_t n, void* stream) {
+  if (int rc = device_check()) return rc;
+  return dense_debug_tanh(kind, x, y, n, static_cast<cudaStream_t>(stream));
 }
 
 size_t vihmc_debug_xgemm_workspace_bytes(int32_t M, int32_t N, int32_t batch) { return dense_xgemm_workspace(M, N, batch); }

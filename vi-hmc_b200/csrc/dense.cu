@@ -496,7 +496,7 @@ static bool fwd3_enabled() {
     const char* e = getenv("VIHMC_DENSE_FWD3");
     return !(e != nullptr && e[0] == '0');
   }();
-  return on && tensor_cores_enabled();
+  return on;   // independent of VIHMC_DENSE_SIMT, so that "exact forward + FP32-SIMT backward" can be measured (error attribution)
 }
 static bool fwd3_eligible(const Stack& s) {
   if (s.n_layers < 2 || s.in_dim > xg::XK) return false;
@@ -982,6 +982,22 @@ int dense_umma_probe(const float* a_img, const float* b_img, unsigned a_lbo, uns
   VIHMC_CUDA_OK(cudaFuncSetAttribute(tc::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kProbeSmem));
   tc::umma_probe_kernel<<<1, 128, tc::kProbeSmem, st>>>(a_img, b_img, a_lbo, a_sbo, b_lbo, b_sbo, a_type, b_type, tc::kIdesc | idesc_extra, out);
   VIHMC_LAUNCH_OK("umma_probe_kernel");
+  return VIHMC_OK;
+}
+
+// vihmc_debug_tanh (include/vihmc.h): the tanh variants of the dense path, evaluated elementwise (bias measurements)
+__global__ void debug_tanh_kernel(int kind, const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i + 1 >= n) return;
+  float a = x[i], b = x[i + 1], ya, yb;
+  if (kind == 0) { ya = tanh_sel(a); yb = tanh_sel(b); }
+  else if (kind == 1) { ya = tanhf(a); yb = tanhf(b); }
+  else { xg::tanh_acc2(a, b, ya, yb); }
+  y[i] = ya; y[i + 1] = yb;
+}
+int dense_debug_tanh(int kind, const float* x, float* y, long long n, cudaStream_t st) {
+  debug_tanh_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, st>>>(kind, x, y, n);
+  VIHMC_LAUNCH_OK("debug_tanh_kernel");
   return VIHMC_OK;
 }
 

@@ -827,8 +827,17 @@ __global__ void rowsum_finish_kernel(const float* __restrict__ part, int splits,
 // The fp32 accumulate of tcgen05.mma truncates toward zero: a chain of k accumulations shrinks the sum by ~k/2 ulp.  At BASELINE
 // size (K = 10201) 1152-deep slices left 1.3e-5 relative error on the trunk's weight gradients (tests/diag_fullsize.py); with
 // 256-deep slices (32 chained accumulations) summed by round-to-nearest adds it is below 4e-6.
-constexpr int kSplitKChunk = 256;       // K slice per CTA once K exceeds kSplitKThreshold
-constexpr int kSplitKThreshold = 512;
+// VIHMC_SPLITK_CHUNK overrides the slice length (A/B runs of accuracy against time).
+inline int splitk_chunk() {
+  static const int v = []() {
+    const char* e = getenv("VIHMC_SPLITK_CHUNK");
+    const int c = e != nullptr ? atoi(e) : 0;
+    return c >= 64 ? c / 16 * 16 : 256;
+  }();
+  return v;
+}
+#define kSplitKChunk (::vihmc::splitk_chunk())          /* K slice per CTA once K exceeds kSplitKThreshold */
+#define kSplitKThreshold (2 * ::vihmc::splitk_chunk())
 
 constexpr int kFillSplitMinK = 512;     // medium reductions are split only to put more CTAs on the GPU (few chains)
 constexpr int kFillSplitMax = 8;
