@@ -1,11 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- chain-grad-evals/sec of the VI-HMC hot path on B200 (BASELINE.json metric).
+"""bench.py -- chain-grad-evals/sec and ESS/sec of the VI-HMC hot path on B200 (BASELINE.json metric).
 
-Workload (N=1): BASELINE.json configs[1] -- Neural_network/VI_HMC: BNN 1-10-10-1 tanh on the bundled
+Headline workload (N=1): BASELINE.json configs[1] -- Neural_network/VI_HMC: BNN 1-10-10-1 tanh on the bundled
 20-point set, HMC over the VI-selected subset (d=40 of D=141, synthetic artefacts of SURVEY.md 8(d)),
 step_size 5e-4, L=196, NLL tau_out=0.0025, 1024 chains per GPU (weak scaling: chains sharded, no
 data-path collective).  One STEP = one HMC iteration (momentum draw, H0, L leapfrog steps, H1,
 Metropolis test, store) of all chains = L+1 = 197 log-posterior gradient evaluations per chain.
+`value` = median over 7 timed launches of `--steps` iterations each.
+
+Further legs in the same JSON line (all independent of --steps):
+  ess      ESS/sec, the metric's second half: BNN chains started from a FITTED variational posterior (vihmc.vi.train_bbb ->
+           vihmc.sensitivity -> the 40 most sensitive coordinates), burn-in, then a timed run; rank-normalised split-R-hat and
+           bulk-ESS over thinned draws, pooled over all ranks' chains (NCCL all-gather of the thinned draws when N > 1)
+  configs  cfg3 (N = 1): BASELINE configs[2], DeepONet full HMC, 256 chains, N=1000 x P=10201, D=172401, L=7, eps=1e-4 as
+           Operator_network/HMC/config_splitting.py states: device value, e2e, roofline against a MEASURED TF32 peak,
+           and the reference's CPU path on this box in both modes BASELINE.md section 3 names
+           cfg4 / cfg5 (N > 1): DeepONet VI-HMC sharded over the GPUs incl. the NCCL gather + global split-R-hat in the
+           e2e clock, and the data-sharded wide BNN (4x512, 100k rows, gradient all-reduce per evaluation: strong scaling)
 
   python bench.py [--gpus N] [--steps K] [--warmup W]         our CUDA engine
   python bench.py --impl reference [--steps K] [--warmup W]   the reference's CPU path (oracle port)
@@ -33,7 +44,17 @@ CHAINS_PER_GPU = 1024
 D_SAMPLED, STEP_SIZE, L_STEPS, TAU_OUT = 40, 5e-4, 196, 0.0025
 FLOP_PER_GRAD_EVAL = 14_000          # 2*[3*N*sum(in*out) - N*in_1*out_1], N=20, 1-10-10-1
 REF_EVALS_PER_STEP = 16              # reference arm: bounded sample = 16 grad-evals per chain per step
+REPS = 7                             # timed launches of the headline leg; value = their median
 WORKLOAD = "bnn_vi_hmc cfg2: 1-10-10-1 tanh, N=20, d=40 of D=141, L=196, eps=5e-4, NLL v=0.0025, 1024 chains/GPU"
+# cfg3: Operator_network/HMC/config_splitting.py (step_size 1e-4, L = int(pi 0.0214^2 / 2e-4) = 7, N_train 1000, p 10201)
+DON_CHAINS, DON_N, DON_NT, DON_NX, DON_L, DON_EPS, DON_SAMPLES = 256, 1000, 101, 101, 7, 1e-4, 3
+DON_GFLOP = 11.557882                # fwd 3.863 + bwd 7.695 GFLOP per chain-grad-eval
+DON_OUT_SCALE = 0.39                 # last branch AND last trunk layer of the teacher scaled by 0.39: targets in the +-0.2 range SURVEY 8(d)
+                                     # specifies (rms 0.18); measured (tools/explore_don_stability.py, profiles/r02_summary.md): the
+                                     # reference's eps = 1e-4 / L = 7 is then a stable leapfrog (acceptance 0.86), whereas the unscaled
+                                     # teacher (outputs of rms 1.3) is stable only below 3e-5
+DON_WORKLOAD = ("deeponet_full_hmc cfg3: branch 101-100x8-100, trunk 5-100x8-100 tanh, D=d=172401, N=1000 functions x P=10201 "
+                "trunk points (synthetic Burgers-shaped, targets in +-0.2), NLL v=1.0, prior_var 0.01, L=7, eps=1e-4, 256 chains")
 
 
 def build_spec():
@@ -60,6 +81,29 @@ def initial_states(mu, sigma, ind, chains, chain0):
     m, s = mu.numpy()[ind], sigma.numpy()[ind]
     for c in range(chains):
         out[c] = m + s * np.random.RandomState(1000 + chain0 + c).randn(len(ind))
+    return torch.from_numpy(out)
+
+
+def don_problem():
+    """cfg3 inputs: synthetic Burgers-shaped data, the full-HMC spec and start points next to the teacher."""
+    import numpy as np
+    import torch
+    from vihmc import synth
+    from vihmc.spec import DeepONetArch, LogProbSpec
+
+    arch = DeepONetArch()
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=DON_N, n_t=DON_NT, n_x=DON_NX, seed=0, out_scale=DON_OUT_SCALE, trunk_scale=DON_OUT_SCALE)
+    spec = LogProbSpec(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
+    return arch, spec, theta
+
+
+def don_starts(theta, chains, chain0=0):
+    import numpy as np
+    import torch
+
+    out = np.empty((chains, theta.numel()), dtype=np.float32)
+    for c in range(chains):
+        out[c] = theta.numpy() + 0.001 * np.random.RandomState(5000 + chain0 + c).randn(theta.numel())
     return torch.from_numpy(out)
 
 
@@ -177,28 +221,260 @@ def run_reference(steps, warmup, n_gpus):
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "step": f"{REF_EVALS_PER_STEP} grad-evals per chain, one chain per core"},
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD + f"; reference arm: a step is a bounded sample of the same trajectory -- a {REF_EVALS_PER_STEP}-gradient-"
+                               "evaluation leapfrog segment per chain instead of all 197 (throughput per evaluation is what is compared)",
+                   "step": f"{REF_EVALS_PER_STEP} grad-evals per chain, one chain per core"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
 
 
+def _don_ref_worker(idx, evals, threads, barrier, out):
+    """cfg3 on the CPU: the restated DeepONet closure (oracle/closures.py, pinned to the reference's closure by the golden vectors)
+    + hamiltorch's params_grad, `evals` gradient evaluations of one chain."""
+    import torch
+    torch.set_num_threads(threads)
+    from oracle import closures as oc
+
+    arch, spec, theta = don_problem()
+    closure = oc.DeepONetLogProb(x1=spec.x.unsqueeze(1), x2=spec.x2.unsqueeze(0), y=spec.y)
+    q = don_starts(theta, 1, idx)[0]
+    oc.value_and_grad(closure, q)          # warm-up (allocator, thread pool)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(evals):
+        _, g = oc.value_and_grad(closure, q)
+        q = q + 1e-4 * g * 1e-6            # keep the arguments changing (no caching anywhere)
+    out[idx] = time.perf_counter() - t0
+    barrier.wait()
+
+
+def run_reference_don(mode, evals):
+    """The reference's CPU path for cfg3 in the two modes BASELINE.md section 3 names: 'intra' = one chain, all cores as
+    intra-op threads; 'procs' = one chain per process with one thread each, all cores."""
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    nproc, threads = (1, cores) if mode == "intra" else (cores, 1)
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(nproc + 1)
+    out = ctx.Array("d", nproc)
+    procs = [ctx.Process(target=_don_ref_worker, args=(i, evals, threads, barrier, out)) for i in range(nproc)]
+    for p in procs:
+        p.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    barrier.wait()
+    wall = time.perf_counter() - t0
+    for p in procs:
+        p.join()
+    return {"value": nproc * evals / wall, "unit": UNIT, "cores": cores, "kind": "port", "mode": mode,
+            "sample": f"{nproc} process(es) x {threads} torch thread(s) x {evals} gradient evaluations of one cfg3 chain each "
+                      f"(N=1000, P=10201, D=172401), torch-eager closure + autograd.grad, {wall:.1f} s"}
+
+
+def _subprocess_json(args, timeout):
+    r = subprocess.run([sys.executable, os.path.abspath(__file__)] + args, capture_output=True, text=True, timeout=timeout,
+                       env={**os.environ, "RANK": "0", "WORLD_SIZE": "1", "CUDA_VISIBLE_DEVICES": ""})
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+
+
 def cpu_baseline_leg():
     """Bounded CPU sample for our arm's JSON line: run the reference arm in a fresh process (no CUDA context)."""
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "60", "--warmup", "3"],
-                           capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
-        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
-        return json.loads(line)["cpu_baseline"]
+        return _subprocess_json(["--impl", "reference", "--steps", "60", "--warmup", "3"], 600)["cpu_baseline"]
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+
+
+def don_cpu_baseline_leg():
+    out = {}
+    for mode, evals in (("intra", 6), ("procs", 2)):
+        try:
+            out[mode] = _subprocess_json(["--impl", "reference-cfg3", "--mode", mode, "--steps", str(evals)], 900)
+        except Exception as e:  # pragma: no cover
+            out[mode] = {"value": None, "unit": UNIT, "kind": "port", "mode": mode, "sample": f"failed: {e}"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(steps, warmup, n_gpus, skip_cpu=False):
+def measure_tf32_peak(dev, seconds=2.0):
+    """cuBLAS TF32 (torch.matmul with allow_tf32) on 8192^3 fp32 operands: best of 10 (burst) and back to back for `seconds`
+    (sustained) -- the same recipe MEASURED_PEAKS.json uses for bf16; the denominator of the tensor-pipe rooflines."""
+    import torch
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        flop = 2.0 * n ** 3
+        return {"tf32_tflops_burst": flop / (best * 1e-3) / 1e12, "tf32_tflops_sustained": flop * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS): best of 10 / {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def ess_leg(dev, rank, world, dist):
+    """ESS/sec at the reference's sampler settings (eps 5e-4, L 196) from a fitted start.  See the module docstring."""
+    import numpy as np
+    import torch
+    from vihmc import diagnostics, engine, samplers, sensitivity, synth, vi
+    from vihmc.spec import LogProbSpec, MLPArch
+
+    BURN, TIMED, THIN = 2000, 5000, 10
+    x, y, xv, yv = synth.bnn_data()
+    arch = MLPArch(in_dim=1, widths=(10, 10), out_dim=1, act="tanh", last_bias=True)
+    mk = lambda a_, b_: LogProbSpec(arch=arch, x=a_, y=b_, loss="NLL", tau_out=0.05 ** 2, prior_sigma_scalar=1.0)
+    t0 = time.perf_counter()
+    fit = vi.train_bbb(mk(x, y), mk(xv, yv), epochs=10_000, num_ens=10, lr_start=1e-2, lr_patience=5000, seed=0)
+    scores = sensitivity.eval_std_dydw((xv, None), arch, fit.best_mu, fit.best_sigma)
+    ind = np.sort(np.argsort(-np.asarray(scores))[:D_SAMPLED]).astype(np.int64)
+    mu, sigma = fit.best_mu, fit.best_sigma
+    numels = arch.tensor_numels()
+    spec = samplers.define_model_log_prob_bnn(arch, "NLL", x, y, numels, None, [torch.tensor(1.0) for _ in numels], TAU_OUT,
+                                              params_mu=mu, params_std=sigma, grad_ind=ind)
+    fit_s = time.perf_counter() - t0
+    chain0 = rank * CHAINS_PER_GPU
+    q0 = initial_states(mu, sigma, ind, CHAINS_PER_GPU, chain0).to(dev)
+    prep = engine.prepare(spec, dev)
+    kw = dict(chain_offset=chain0, diagnostics=True, to_host=False, hamiltorch_fallback_rule=False)
+    burn = engine.run_sampler([prep], q0, BURN, L_STEPS, STEP_SIZE, burn=BURN - 2, seed=11, **kw)
+    q1 = burn.samples[-1].contiguous()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = engine.run_sampler([prep], q1, TIMED, L_STEPS, STEP_SIZE, burn=0, seed=12, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+    draws, lp = res.samples[::THIN].contiguous(), res.logp[::THIN].contiguous()
+    acc = res.accepted.float().mean().reshape(1)
+    tg0 = time.perf_counter()
+    if world > 1:   # pool the thinned draws of every rank's chains on all ranks (NCCL all-gather), timing = max over ranks
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dl = [torch.empty_like(draws) for _ in range(world)]
+        ll = [torch.empty_like(lp) for _ in range(world)]
+        dist.all_gather(dl, draws)
+        dist.all_gather(ll, lp)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        acc /= world
+        draws, lp = torch.cat(dl, 1), torch.cat(ll, 1)
+    summ = diagnostics.summarize(draws, logp=lp) if rank == 0 else None
+    torch.cuda.synchronize()
+    gather_diag_s = time.perf_counter() - tg0
+    if rank != 0:
+        return None
+    secs = float(t.item())
+    return {"definition": "bulk-ESS, rank-normalised, split chains (Vehtari et al. 2021); min / median over the d sampled coordinates, chains "
+                          "of all ranks pooled; per second of the device-timed sampling run (max over ranks)",
+            "start": f"fitted variational posterior: vihmc.vi.train_bbb (10k epochs x 10 draws) -> vihmc.sensitivity scores -> the {D_SAMPLED} "
+                     f"most sensitive of 141 weights, q0 = mu + sigma z ({fit_s:.1f} s incl. selection)",
+            "chains": int(summ["chains"]), "burn_in_iterations": BURN, "timed_iterations": TIMED, "thin": THIN,
+            "post_burn_draws_per_chain": int(summ["draws"]), "seconds": secs, "acceptance_rate": float(acc.item()),
+            "rhat_max": float(summ["rhat_max"]), "rhat_median": float(summ["rhat_median"]), "rhat_logp": float(summ["rhat_logp"]),
+            "ess_bulk_min": float(summ["ess_bulk_min"]), "ess_bulk_median": float(summ["ess_bulk_median"]),
+            "ess_bulk_logp": float(summ["ess_bulk_logp"]),
+            "ess_min_per_sec": float(summ["ess_bulk_min"]) / secs, "ess_median_per_sec": float(summ["ess_bulk_median"]) / secs,
+            "stationary": bool(summ["rhat_max"] < 1.01),
+            "gather_and_diagnostics_seconds": gather_diag_s,
+            "note": "the posterior over the selected BNN weights is multi-modal: between 25k and 150k iterations of 1024 chains the "
+                    "rank-normalised split-R-hat stays at 2.3-2.6 while the mean log-posterior still drifts (profiles/r02_ess2.log), so no "
+                    "budget a bench can afford reaches R-hat < 1.01 at the reference's eps / L; the ESS is reported as measured, with its R-hat"}
+
+
+def don_leg(dev, peaks_tf32, skip_cpu):
+    """cfg3 (BASELINE configs[2]): DeepONet full HMC on one GPU -- device-timed, end to end, roofline, CPU baseline."""
+    import torch
+    from vihmc import engine, samplers
+
+    arch, spec, theta = don_problem()
+    q0_host = don_starts(theta, DON_CHAINS)
+    prep = engine.prepare(spec, dev)
+    q0 = q0_host.to(dev)
+    evals = DON_CHAINS * DON_SAMPLES * (DON_L + 1)
+    engine.run_sampler([prep], q0, 1, 1, DON_EPS, to_host=False)             # warm-up: workspace, kernel attributes
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = engine.run_sampler([prep], q0, DON_SAMPLES, DON_L, DON_EPS, burn=0, seed=2, to_host=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = evals / (ms * 1e-3)
+    acc = float(res.accepted.float().mean())
+    dH = float((res.hamiltonians[..., 0] - res.hamiltonians[..., 1]).abs().median())
+    del res
+    # a gradient batch alone (what the FLOP count refers to)
+    engine.logp_grad(prep, q0)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(2):
+        engine.logp_grad(prep, q0)
+    g1.record()
+    torch.cuda.synchronize()
+    grad_ms = g0.elapsed_time(g1) / 2
+    tflops = DON_GFLOP * DON_CHAINS / (grad_ms * 1e-3) / 1e3
+    # end to end: host tensors in, host samples out
+    samplers.sample(spec, q0_host[:8], num_samples=1, num_steps_per_sample=1, step_size=DON_EPS)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = samplers.sample(spec, q0_host, num_samples=DON_SAMPLES, num_steps_per_sample=DON_L, step_size=DON_EPS, seed=3, return_result=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(t.numel() * t.element_size() for t in (spec.x, spec.x2, spec.y, q0_host))
+    d2h = sum(x.numel() * x.element_size() for x in (out.samples, out.accepted, out.hamiltonians, out.logp, out.step_sizes))
+    peak = peaks_tf32["tf32_tflops_sustained"]
+    leg = {
+        "workload": DON_WORKLOAD, "metric": METRIC, "unit": UNIT, "value": value, "ms_per_step": ms / DON_SAMPLES,
+        "step": f"one HMC iteration of all {DON_CHAINS} chains = L+1 = {DON_L + 1} grad-evals per chain; {DON_SAMPLES} timed iterations",
+        "acceptance_rate": acc, "median_abs_energy_error": dH,
+        "e2e": {"value": evals / e2e_s, "unit": UNIT, "seconds": e2e_s, "h2d_bytes_per_step": h2d / DON_SAMPLES,
+                "d2h_bytes_per_step": d2h / DON_SAMPLES},
+        "gradient_batch": {"chains": DON_CHAINS, "ms": grad_ms, "chain_grad_evals_per_s": DON_CHAINS / (grad_ms * 1e-3),
+                           "tflops_fp32_equivalent": tflops},
+        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
+                     "kernel": "whole gradient batch (launch list and per-kernel ncu: profiles/r02_summary.md section B)",
+                     "note": "achieved = 11.56 GFLOP of fp32-equivalent work per chain-grad-eval (SURVEY 8(d)) / CUDA-event time of a "
+                             "256-chain gradient batch; peak = cuBLAS TF32 8192^3 sustained, measured in this run (tf32_peak).  The tensor "
+                             "core executes 3 tf32 products per fp32 product in the backward pass and 9 bf16 products (exact fixed-point "
+                             "accumulation, csrc/xgemm.cuh) in the forward pass, i.e. >= 3x the algorithmic FLOPs"},
+        "tf32_peak": peaks_tf32,
+        "cpu_baseline": None if skip_cpu else don_cpu_baseline_leg(),
+    }
+    return leg
+
+
+def run_ours(steps, warmup, n_gpus, skip_cpu=False, legs="all"):
+    import statistics
+
     import torch
     import torch.distributed as dist
     from vihmc import engine, samplers
@@ -233,7 +509,7 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
         return engine.run_sampler([prep], q0, n_samples, L_STEPS, STEP_SIZE, burn=0, seed=seed, chain_offset=chain0,
                                   diagnostics=True, to_host=False)
 
-    # ---- device-timed: inputs resident in HBM, one persistent launch of `steps` iterations ----
+    # ---- device-timed: inputs resident in HBM; REPS timed launches of `steps` iterations each, value = median ----
     launch(warmup, seed=1)
     torch.cuda.synchronize()
     # the sampler allocates its result tensors with torch.empty: put blocks of those sizes into torch's caching allocator
@@ -242,62 +518,64 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
             torch.empty((steps, CHAINS_PER_GPU), device=dev), torch.empty((steps, CHAINS_PER_GPU), dtype=torch.uint8, device=dev),
             torch.empty(CHAINS_PER_GPU, device=dev)]
     del warm
-    flush.fill_(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    torch.cuda.synchronize()
+    times, acc_rate = [], 0.0
     with ClockSampler(local_rank) as clk:
-        e0.record()
-        res = launch(steps, seed=2)
-        e1.record()
-        torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        for rep in range(REPS):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            res = launch(steps, seed=2 + rep)
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+            acc_rate = float(res.accepted.float().mean())
+            del res
+    ms = statistics.median(times)
     evals = world * CHAINS_PER_GPU * steps * (L_STEPS + 1)
     value = evals / (ms * 1e-3)
-    acc_rate = float(res.accepted.float().mean())
-    # ESS/s (the metric's second half): rank-normalised split-R-hat / bulk-ESS (vihmc.diagnostics, Vehtari et al. 2021)
-    # over the post-burn draws of THIS rank's chains (burn = steps // 5 as cfg.burn = num_samples // 5), per second of
-    # the device-timed run; summed over ranks because chains are independent.
-    ess = None
-    if steps >= 40:
-        from vihmc import diagnostics
-        burn_rows = steps // 5
-        summ = diagnostics.summarize(res.samples[burn_rows:], logp=res.logp[burn_rows:])
-        t_ess = torch.tensor([summ["ess_bulk_min"], summ["ess_bulk_median"], summ["ess_bulk_logp"]], device=dev, dtype=torch.float64)
-        t_rhat = torch.tensor([summ["rhat_max"]], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_ess, op=dist.ReduceOp.SUM)
-            dist.all_reduce(t_rhat, op=dist.ReduceOp.MAX)
-        ess = {"definition": "bulk-ESS, rank-normalised, split chains; min / median over the d sampled coordinates, chains pooled",
-               "post_burn_draws": int(summ["draws"]), "chains": int(summ["chains"]) * world,
-               "ess_bulk_min": float(t_ess[0]), "ess_bulk_median": float(t_ess[1]), "ess_bulk_logp": float(t_ess[2]),
-               "rhat_max": float(t_rhat[0]),
-               "ess_min_per_sec": float(t_ess[0]) / (ms * 1e-3), "ess_median_per_sec": float(t_ess[1]) / (ms * 1e-3)}
 
     # ---- end to end through the public API: host tensors in, host samples out, every call ----
-    # warm-up call of the SAME shape as the timed one: the pinned result buffers (53 MB at 300 iterations) then come out of
-    # torch's caching host allocator instead of a fresh cudaHostAlloc (page-locking 53 MB costs ~0.1 s on a fresh box)
+    # warm-up call of the SAME shape as the timed one: the pinned result buffers then come out of torch's caching host allocator
+    # instead of a fresh cudaHostAlloc (page-locking tens of MB costs ~0.1 s on a fresh box)
     samplers.sample(spec, q0_host, num_samples=steps, num_steps_per_sample=L_STEPS, step_size=STEP_SIZE, seed=3,
                     chain_offset=chain0)
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = samplers.sample(spec, q0_host, num_samples=steps, num_steps_per_sample=L_STEPS, step_size=STEP_SIZE, seed=4,
-                          chain_offset=chain0, return_result=True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_times, out = [], None
+    for rep in range(3):
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = samplers.sample(spec, q0_host, num_samples=steps, num_steps_per_sample=L_STEPS, step_size=STEP_SIZE, seed=4 + rep,
+                              chain_offset=chain0, return_result=True)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_times.append(float(t.item()))
+    e2e_s = statistics.median(e2e_times)
     h2d = prep.h2d_bytes + q0_host.numel() * 4
     d2h = sum(x.numel() * x.element_size() for x in (out.samples, out.accepted, out.hamiltonians, out.logp, out.step_sizes))
     e2e_value = evals / e2e_s
+    del out
+
+    # ---- ESS/sec ----
+    ess = ess_leg(dev, rank, world, dist) if legs in ("all", "ess") else None
+
+    # ---- the other BASELINE configs ----
+    configs = {}
+    if legs in ("all", "configs"):
+        if world == 1:
+            tf32 = measure_tf32_peak(dev)
+            configs["cfg3"] = don_leg(dev, tf32, skip_cpu)
+        else:
+            from bench_multi import cfg4_leg, cfg5_leg   # tools-free: lives next to this file
+            configs["cfg4"] = cfg4_leg(dev, rank, world, dist)
+            configs["cfg5"] = cfg5_leg(dev, rank, world, dist)
 
     if rank != 0:
         if world > 1:
@@ -317,8 +595,11 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "chains_total": world * CHAINS_PER_GPU,
                    "step": "one HMC iteration of all chains = L+1 = 197 grad-evals per chain",
-                   "l2": "256 MB flush before the timed launch; chain state is shared-memory resident",
+                   "timing": f"median of {REPS} launches of {steps} iterations each (CUDA events, max over ranks per launch); "
+                             f"ms of every launch in launch_ms",
+                   "l2": "256 MB flush before every timed launch; chain state is shared-memory resident",
                    "parallelism": f"chains sharded {world}x{CHAINS_PER_GPU}, no data-path collective"},
+        "launch_ms": times,
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
                      "kernel": "mlp_small_sample_kernel<W=10, warps/chain=1, specialised>",
@@ -338,11 +619,12 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
                                   "wavefronts_per_chain_grad_eval": 303.0},
         "cpu_baseline": cpu_baseline_leg() if (world == 1 and not skip_cpu) else None,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
-                "seconds": e2e_s},
+                "seconds": e2e_s, "timing": "median of 3 calls of samplers.sample with host tensors"},
         "gpu_launches": 1,
         "clocks": clk.summary(),
         "acceptance_rate": acc_rate,
         "ess": ess,
+        "configs": configs,
     }
     if world > 1:
         dist.destroy_process_group()
@@ -352,12 +634,19 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cfg3"])
+    ap.add_argument("--mode", default="intra", choices=["intra", "procs"], help="--impl reference-cfg3 only")
+    ap.add_argument("--legs", default="all", choices=["all", "main", "ess", "configs"], help="profiling runs: restrict the extra legs")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     a = ap.parse_args()
-    line = run_reference(a.steps, a.warmup, a.gpus) if a.impl == "reference" else run_ours(a.steps, a.warmup, a.gpus, a.skip_cpu_baseline)
+    if a.impl == "reference":
+        line = run_reference(a.steps, a.warmup, a.gpus)
+    elif a.impl == "reference-cfg3":
+        line = run_reference_don(a.mode, a.steps)
+    else:
+        line = run_ours(a.steps, a.warmup, a.gpus, a.skip_cpu_baseline, a.legs)
     if line is not None:
         if _REAL_STDOUT_FD is not None:
             os.write(_REAL_STDOUT_FD, (json.dumps(line) + "\n").encode())

@@ -102,6 +102,8 @@ typedef struct vihmc_problem {
   const int64_t* sens_ind;            /* [d] or NULL */
   const float* prior_mu;              /* [d] or NULL (zero) */
   const float* prior_sigma;           /* [d] or NULL (scalar) */
+  int64_t frozen_chain_stride;        /* 0: frozen[D] is shared by every chain; D: frozen[C, D], one row per chain (the per-sample
+                                         VI redraw, my_make_func.py:45-50: every chain then holds its own draw of the frozen weights) */
 } vihmc_problem;
 
 /*
@@ -130,6 +132,13 @@ typedef struct vihmc_sampler_io {
   float* step_sizes;          /* [C] in: ignored; out: final (adapted) step size per chain */
   const float* inject_momenta;  /* [num_samples, C, d] replaces the Philox N(0,1) draws */
   const float* inject_uniforms; /* [num_samples, C] replaces the Philox U(0,1) draws */
+  /* Per-sample VI redraw -- the reference's `sample_weights` hook (Neural_network/VI_HMC/my_make_func.py:45-50,
+   * Operator_network/VI_HMC/my_make_func.py:38-42; trigger main_VI_HMC.py:96-99): at the start of every iteration ALL D frozen
+   * weights of every chain are redrawn, W = mu + sigma z with mu = prob->frozen, z ~ N(0,1) from Philox stream 2 (the same draws
+   * as vihmc_vi_redraw_philox), and the sampled coordinates are scattered on top.  Enabled by vi_sigma != NULL (needs frozen). */
+  const float* vi_sigma;          /* [D] variational standard deviations */
+  float* vi_params;               /* [num_samples, C, D] out (optional): the redrawn weight vectors, what the hook appends to vi_params */
+  const float* inject_vi_normals; /* [num_samples, C, D] replaces the Philox N(0,1) draws of the redraw */
 } vihmc_sampler_io;
 
 VIHMC_API const char* vihmc_version(void);

@@ -438,3 +438,72 @@ def test_validation_step_bnn_regression_and_nll():
         lp, mse = validate.sample_log_prob_and_mse(spec, q, x=xv, y=yv)
         np.testing.assert_allclose(mse.numpy(), want.numpy(), rtol=2e-5)
         np.testing.assert_allclose(lp.numpy(), torch.stack(logp).numpy(), rtol=1e-6)
+
+
+def _oracle_redraw_chain(closure, mu, sigma, q0, S, L, eps, momenta, normals):
+    """What a sampler does that fires the reference's hook `log_prob_func(params, True)` once per sample (main_VI_HMC.py:96-99 ->
+    my_make_func.py:45-50): redraw ALL frozen weights, then one hamiltorch iteration on the redrawn closure.  Every proposal is
+    accepted here (the test injects u = 1e-30), so the chain is the sequence of trajectory end points."""
+    q = q0.clone()
+    states, H0s, H1s = [], [], []
+    for n in range(S):
+        closure.frozen = (mu.double() + sigma.double() * normals[n].double()).to(closure.dtype)
+        p = momenta[n].to(closure.dtype)
+        H0s.append(float(hr.hamiltonian(q, p, closure)))
+        q, p1 = hr.leapfrog(q, p, closure, L, eps)
+        H1s.append(float(hr.hamiltonian(q, p1, closure)))
+        states.append(q.clone())
+    return torch.stack(states), np.array(H0s), np.array(H1s)
+
+
+@pytest.mark.parametrize("force_general", [False, True])
+def test_vi_redraw_hook_matches_oracle(force_general):
+    """a9: per-sample VI redraw (my_make_func.py:45-50) inside the persistent kernel and inside the general sampler, against the
+    oracle fed the same normals; the redrawn weight vectors come back as vi_params."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    d, D, S, L, eps, Cn = case["d"], 141, 4, 5, 5e-4, 2
+    rs = np.random.RandomState(31)
+    q0 = torch.from_numpy(case["q"][:Cn])
+    p = torch.from_numpy(rs.randn(S, Cn, d).astype(np.float32))
+    z = torch.from_numpy(rs.randn(S, Cn, D).astype(np.float32))
+    u = torch.full((S, Cn), 1e-30)
+    res = engine.run_sampler([spec], q0, S, L, eps, inject_momenta=p, inject_uniforms=u, vi_redraw=True, inject_vi_normals=z,
+                             force_general=force_general)
+    want = case["mu"][None, None] + case["sigma"][None, None] * z
+    np.testing.assert_allclose(res.vi_params.numpy(), want.numpy(), rtol=1e-6, atol=1e-7)
+    assert bool(res.accepted.all())
+    for c in range(Cn):
+        closure = cases.bnn_oracle(case, dtype=torch.float64)
+        states, H0, H1 = _oracle_redraw_chain(closure, case["mu"], case["sigma"], q0[c].double(), S, L, eps, p[:, c], z[:, c])
+        np.testing.assert_allclose(res.hamiltonians[:, c, 0].numpy(), H0, rtol=RTOL)
+        np.testing.assert_allclose(res.hamiltonians[:, c, 1].numpy(), H1, rtol=RTOL)
+        # stored rows: row 0 = params_init, row n = state after iteration n (hamiltorch's n > burn rule, burn = 0)
+        np.testing.assert_allclose(res.samples[1:, c].numpy(), states[1:].numpy(), rtol=1e-4, atol=1e-4)
+    # the redraw changes the chain: without it the same momenta give different Hamiltonians
+    plain = engine.run_sampler([spec], q0, S, L, eps, inject_momenta=p, inject_uniforms=u, force_general=force_general)
+    assert not np.allclose(plain.hamiltonians.numpy(), res.hamiltonians.numpy(), rtol=1e-4)
+
+
+def test_vi_redraw_philox_stream_and_file(tmp_path, monkeypatch):
+    """Without injection the redraw uses Philox stream 2 keyed on (seed, global chain, iteration): bit-identical to the exported
+    building block vihmc_vi_redraw_philox, identical in the persistent kernel and the general sampler, invariant to sharding; and
+    samplers.sample(..., vi_redraw=True, vi_params_uid=...) writes vi_params_<uid>.npy as the reference's hook does."""
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    spec = cases.bnn_spec(case)
+    q0 = torch.from_numpy(case["q"][:4])
+    kw = dict(num_samples=3, num_steps=4, step_size=5e-4, seed=77, vi_redraw=True)
+    a = engine.run_sampler([spec], q0, **kw)
+    b = engine.run_sampler([spec], q0, force_general=True, **kw)
+    assert torch.equal(a.vi_params, b.vi_params)
+    for n in range(3):
+        blk = engine.vi_redraw_philox(77, n, 0, 4, case["mu"], case["sigma"]).cpu()
+        assert torch.equal(a.vi_params[n], blk)
+    hi = engine.run_sampler([spec], q0[2:], chain_offset=2, **kw)
+    assert torch.equal(hi.vi_params, a.vi_params[:, 2:]) and torch.equal(hi.samples, a.samples[:, 2:])
+    monkeypatch.chdir(tmp_path)
+    out = samplers.sample(spec, q0[0], num_samples=3, num_steps_per_sample=4, step_size=5e-4, seed=77, vi_redraw=True, vi_params_uid="t1")
+    saved = np.load(tmp_path / "vi_params_t1.npy")
+    assert saved.shape == (3, 141) and np.array_equal(saved, a.vi_params[:, 0].numpy()) and len(out) == 3

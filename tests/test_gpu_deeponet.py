@@ -375,3 +375,31 @@ def test_trunk_subsampling_closure_calls_match_the_restated_sampler():
     res2 = samplers.sample(spec, q0, num_samples=2, num_steps_per_sample=L, step_size=eps, inject_momenta=p[:2], inject_uniforms=u[:2],
                            return_result=True)
     assert not np.allclose(res2.hamiltonians[0, 0].numpy(), res.hamiltonians[0, 0].numpy(), rtol=1e-7)
+
+
+def test_vi_redraw_hook_deeponet_matches_oracle():
+    """a9 for the operator network (Operator_network/VI_HMC/my_make_func.py:38-42): per-sample redraw of all frozen weights in the
+    general sampler (every chain evaluates the closure on its own draw: vihmc_problem.frozen_chain_stride), against the oracle."""
+    inp = cases.don_inputs("small")
+    spec = cases.don_spec(inp, "vi")
+    d, D, S, L, eps, Cn = len(inp["ind"]), inp["arch"].num_params, 3, 3, 1e-4, 2
+    rs = np.random.RandomState(5)
+    q0 = (inp["mu"][inp["ind"]][None] + 0.01 * torch.from_numpy(rs.randn(Cn, d).astype(np.float32)))
+    p = torch.from_numpy(rs.randn(S, Cn, d).astype(np.float32))
+    z = torch.from_numpy(rs.randn(S, Cn, D).astype(np.float32))
+    u = torch.full((S, Cn), 1e-30)
+    res = engine.run_sampler([spec], q0, S, L, eps, inject_momenta=p, inject_uniforms=u, vi_redraw=True, inject_vi_normals=z)
+    want = inp["mu"][None, None] + inp["sigma"][None, None] * z
+    np.testing.assert_allclose(res.vi_params.numpy(), want.numpy(), rtol=1e-6, atol=1e-7)
+    for c in range(Cn):
+        closure = cases.don_oracle(inp, "vi", dtype=torch.float64)
+        q = q0[c].double()
+        for n in range(S):
+            closure.frozen = inp["mu"].double() + inp["sigma"].double() * z[n, c].double()
+            H0 = float(hr.hamiltonian(q, p[n, c].double(), closure))
+            q, p1 = hr.leapfrog(q, p[n, c].double(), closure, L, eps)
+            H1 = float(hr.hamiltonian(q, p1, closure))
+            assert abs(float(res.hamiltonians[n, c, 0]) - H0) <= 2e-5 * abs(H0) + 1e-3
+            assert abs(float(res.hamiltonians[n, c, 1]) - H1) <= 2e-5 * abs(H1) + 1e-3
+            if n >= 1:
+                np.testing.assert_allclose(res.samples[n, c].numpy(), q.numpy(), rtol=1e-4, atol=1e-5)

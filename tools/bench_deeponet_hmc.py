@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--samples", type=int, default=3)
     ap.add_argument("--mode", default="full", choices=["full", "split", "vi"])
     ap.add_argument("--n", type=int, default=1000)
+    ap.add_argument("--out-scale", type=float, default=1.0, help="synth.burgers_like(out_scale=...): 0.15 = targets in the +-0.2 range")
+    ap.add_argument("--q0-noise", type=float, default=0.001)
     ap.add_argument("--eps", type=float, default=3e-5,
                     help="step size.  The reference config's 1e-4 is tuned for its trained net; on the synthetic teacher problem the "
                          "leapfrog is unstable above ~3e-5 (non-finite H1 => every proposal rejected, as hamiltorch would)")
@@ -30,7 +32,7 @@ def main():
     rs = np.random.RandomState(0)
     P = 101 * 101
     # teacher-generated Burgers-shaped data: chains start next to theta*; the default step size 3e-5 is stable there (1e-4 is not, see --eps)
-    x1, x2, y, theta = synth.burgers_like(arch, n_train=a.n, n_t=101, n_x=101, seed=0)
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=a.n, n_t=101, n_x=101, seed=0, out_scale=a.out_scale)
     kw = dict(arch=arch, x2=x2, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1)
     L, eps = 7, a.eps
     if a.mode == "vi":
@@ -47,7 +49,7 @@ def main():
         spec = LogProbSpec(x=x1, y=y, **kw)
         q0 = theta[None].repeat(a.chains, 1)
         integ, evals = samplers.Integrator.IMPLICIT, a.samples * (L + 1)
-    q0 = q0 + 0.001 * torch.from_numpy(rs.randn(*q0.shape).astype(np.float32))
+    q0 = q0 + a.q0_noise * torch.from_numpy(rs.randn(*q0.shape).astype(np.float32))
     samplers.sample(spec, q0, num_samples=1, num_steps_per_sample=1, step_size=eps, integrator=integ)   # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -109,6 +109,13 @@ __global__ void add_rows_kernel(float* __restrict__ acc, const float* __restrict
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) acc[c] = first ? v[c] : acc[c] + v[c];
 }
+// W[c, f] = mu[f] + sigma[f] z[c, f] with injected normals (the Philox form is vi_redraw_kernel in elementwise.cu)
+__global__ void vi_apply_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ z, long long C,
+                                long long D, float* __restrict__ W) {
+  const long long total = C * D;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+    W[t] = fmaf(__ldg(sigma + t % D), z[t], __ldg(mu + t % D));
+}
 __global__ void fill_kernel(float* __restrict__ dst, float v, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;
@@ -166,9 +173,10 @@ static size_t model_workspace(const vihmc_problem* p, long long C) {
   return dense_workspace_bytes(p, C);
 }
 
-static size_t sampler_state_bytes(long long C, long long d) {
+static size_t sampler_state_bytes(long long C, long long d, long long D_redraw = 0) {
   size_t rows = 5;  // p, g, q_prop, q_cur, q_fb
   size_t bytes = rows * ((size_t)C * d * sizeof(float) + 256);
+  bytes += (size_t)C * D_redraw * sizeof(float) + 256;                     // per-chain frozen weights of the VI redraw
   bytes += 16 * ((size_t)C * sizeof(float) + 256);                         // per-chain scalars
   bytes += (size_t)C * row_partials(d) * sizeof(float) + 256;              // ke partials
   return bytes;
@@ -234,7 +242,7 @@ double vihmc_prior_log_norm(const float* sigma_host, int64_t d, float sigma_scal
 
 size_t vihmc_workspace_bytes(const vihmc_problem* prob, int64_t C) {
   if (check_problem(prob) != VIHMC_OK || C < 1) return 0;
-  return model_workspace(prob, C) + sampler_state_bytes(C, prob->d) + 4096;
+  return model_workspace(prob, C) + sampler_state_bytes(C, prob->d, prob->frozen != nullptr ? prob->D : 0) + 4096;
 }
 
 int vihmc_logp_grad(const vihmc_problem* prob, int64_t C, const float* q, float* logp, float* grad, void* workspace,
@@ -298,9 +306,15 @@ int vihmc_sample(const vihmc_problem* probs, int32_t n_problems, const vihmc_sam
     const size_t b = model_workspace(&probs[m], C);
     model_ws = b > model_ws ? b : model_ws;
   }
-  if (workspace_bytes < model_ws + sampler_state_bytes(C, d) + 4096 || (workspace == nullptr))
+  const bool redraw = io != nullptr && io->vi_sigma != nullptr;
+  const long long Dfull = probs[0].D;
+  if (redraw)
+    for (int m = 0; m < M; ++m)
+      if (probs[m].frozen == nullptr || probs[m].frozen_chain_stride != 0)
+        return fail(VIHMC_ERR_INVALID, "the VI redraw needs the shared variational means (prob->frozen[D]) and sens_ind");
+  if (workspace_bytes < model_ws + sampler_state_bytes(C, d, redraw ? Dfull : 0) + 4096 || (workspace == nullptr))
     return fail(VIHMC_ERR_WORKSPACE, "workspace too small: have %zu bytes, need %zu", workspace_bytes,
-                model_ws + sampler_state_bytes(C, d) + 4096);
+                model_ws + sampler_state_bytes(C, d, redraw ? Dfull : 0) + 4096);
   Carver cv(workspace, workspace_bytes);
   const size_t cd = (size_t)C * d;
   float* p = cv.take<float>(cd);
@@ -321,7 +335,17 @@ int vihmc_sample(const vihmc_problem* probs, int32_t n_problems, const vihmc_sam
   float* Ht = cv.take<float>(C);
   const int np = row_partials(d);
   float* ke_part = cv.take<float>((size_t)C * np);
+  float* Wred = redraw ? cv.take<float>((size_t)C * Dfull) : nullptr;
   void* mws = cv.take<char>(model_ws);
+  // with the redraw every chain evaluates the closures on its own draw of the frozen weights
+  vihmc_problem local[16];
+  if (M > 16) return fail(VIHMC_ERR_UNSUPPORTED, "more than 16 split closures");
+  for (int m = 0; m < M; ++m) {
+    local[m] = probs[m];
+    if (redraw) { local[m].frozen = Wred; local[m].frozen_chain_stride = Dfull; }
+  }
+  const float* redraw_mu = probs[0].frozen;   // the variational means (shared by the closures)
+  probs = local;
   const int cb = blocks_for(C);
 
   VIHMC_CUDA_OK(cudaMemcpyAsync(q_cur, q0, cd * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -345,6 +369,14 @@ int vihmc_sample(const vihmc_problem* probs, int32_t n_problems, const vihmc_sam
     if (cfg->hamiltorch_fallback_rule && n == burn + 1) {
       VIHMC_CUDA_OK(cudaMemcpyAsync(q_fb, q0, cd * sizeof(float), cudaMemcpyDeviceToDevice, st));
       VIHMC_CUDA_OK(cudaMemcpyAsync(logp_fb, logp_init, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (redraw) {   // my_make_func.py:45-50: all D frozen weights of every chain = mu + sigma z
+      if (io->inject_vi_normals != nullptr) {
+        vi_apply_kernel<<<blocks_for(C * Dfull), 128, 0, st>>>(redraw_mu, io->vi_sigma, io->inject_vi_normals + (size_t)n * C * Dfull, C, Dfull, Wred);
+        VIHMC_LAUNCH_OK("vi_apply_kernel");
+      } else if (int rc = launch_vi_redraw(cfg->seed, n, cfg->chain_offset, C, Dfull, redraw_mu, io->vi_sigma, Wred, st)) return rc;
+      if (io->vi_params != nullptr)
+        VIHMC_CUDA_OK(cudaMemcpyAsync(io->vi_params + (size_t)n * C * Dfull, Wred, (size_t)C * Dfull * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     // momentum + its kinetic energy
     if (io != nullptr && io->inject_momenta != nullptr)

@@ -553,6 +553,8 @@ static int launch_head3(const DensePlan& pl, int Cb, const unsigned char* a_img,
   a.tiles_per_chunk = (int)((a.p_tiles + want - 1) / want);
   a.p_chunks = (a.p_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
   a.parts = a.m_tiles * a.p_chunks;
+  static const int ahead = []() { const char* e = getenv("VIHMC_HEAD_PREFETCH"); return e != nullptr ? atoi(e) : 0; }();
+  a.prefetch_ahead = ahead;
   a.n_items = (long long)Cb * a.parts;
   if (parts_out != nullptr) *parts_out = a.parts;
   const unsigned grid = (unsigned)(a.n_items < sms ? a.n_items : sms);
@@ -787,7 +789,7 @@ static int prepare_shared(const vihmc_problem* p, const DensePlan& pl, void* ws,
 
 // Wf[c] = padded(frozen with q scattered at sens_ind)   (my_make_func.py:48-50 / :56-57)
 static int scatter_padded(const vihmc_problem* p, const DensePlan& pl, const int* pad_map, const float* qb, float* Wf, int Cb,
-                          cudaStream_t st) {
+                          cudaStream_t st, long long c0 = 0) {
   const long long D = pl.D, d = p->d;
   const unsigned gx = (unsigned)((D + 1023) / 1024 < 148 * 4 ? (D + 1023) / 1024 : 148 * 4);
   if (p->frozen == nullptr) {
@@ -795,7 +797,8 @@ static int scatter_padded(const vihmc_problem* p, const DensePlan& pl, const int
     VIHMC_LAUNCH_OK("scatter_fill_padded_kernel");
     return VIHMC_OK;
   }
-  scatter_fill_padded_kernel<<<dim3(gx, Cb), 256, 0, st>>>(p->frozen, 0, pad_map, Wf, D, pl.Dp);
+  // frozen_chain_stride != 0: every chain has its own row of frozen weights (per-sample VI redraw)
+  scatter_fill_padded_kernel<<<dim3(gx, Cb), 256, 0, st>>>(p->frozen + c0 * p->frozen_chain_stride, p->frozen_chain_stride, pad_map, Wf, D, pl.Dp);
   VIHMC_LAUNCH_OK("scatter_fill_padded_kernel");
   const unsigned gd = (unsigned)((d + 1023) / 1024 < 148 * 4 ? (d + 1023) / 1024 : 148 * 4);
   scatter_put_padded_kernel<<<dim3(gd, Cb), 256, 0, st>>>(reinterpret_cast<const long long*>(p->sens_ind), qb, pad_map, Wf, d, pl.Dp);
@@ -873,7 +876,7 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
     }
     const float* qb = q + c0 * d;
 
-    if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st)) return rc;
+    if (int rc = scatter_padded(p, pl, sb.pad_map, qb, Wf, Cb, st, c0)) return rc;
     if (pl.fwd3) {
       if (int rc = stack_forward3(pl.a, p->x, N, Wf, Dp, acts_a, p->act, Cb, wimg3, ximg_a, xsc_a, st)) return rc;
       if (int rc = stack_forward3(pl.b, trunk_in, P, Wf, Dp, acts_b, p->act, Cb, wimg3, ximg_b, xsc_b, st)) return rc;
@@ -1056,7 +1059,7 @@ int dense_predict(const vihmc_problem* p, long long C, const float* q, float* ou
     for (int l = 0; l < pl.b.n_layers; ++l) acts_b[l] = bb.take((long long)Cb * P * pl.b.dims[l]);
     float* part = bb.take(2LL * Cb * pl.head_tiles);
     float* img = pl.img_floats > 0 ? bb.take((long long)Cb * pl.img_floats) : nullptr;
-    if (int rc = scatter_padded(p, pl, sb.pad_map, q + c0 * d, Wf, Cb, st)) return rc;
+    if (int rc = scatter_padded(p, pl, sb.pad_map, q + c0 * d, Wf, Cb, st, c0)) return rc;
     if (pl.fwd3) {   // exact-accumulation forward: stacks, then the head kernel in predict mode writes out[c, n, p] directly
       unsigned char* wimg3 = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.wimg3_floats));
       unsigned char* ximg_a = reinterpret_cast<unsigned char*>(bb.take((long long)Cb * pl.ximg_a_floats));

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) fused_forward3_kernel(Fwd3Args 
 // ---------------------------------------------------------------------------------------------------------------
 // head: persistent, warp-specialised
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int H3_THREADS = 320;                      // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int H3_THREADS = 576;                      // warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue
 constexpr int H3_BN = 64;                            // trunk points per tile
 constexpr int H3_BPIECE = (H3_BN / 8) * XRG;         // 14 336 B: one piece of a 64-row B tile
 constexpr int H3_BTILE = 3 * H3_BPIECE;              // 43 008 B
@@ -458,7 +458,7 @@ constexpr int H3_B_OFF = XTILE;
 constexpr int H3_STAGE_OFF = H3_B_OFF + 2 * H3_BTILE;
 constexpr int H3_SA_OFF = H3_STAGE_OFF + 128 * H3_LD * 4;
 constexpr int H3_RED_OFF = H3_SA_OFF + 512;
-constexpr int H3_BAR_OFF = H3_RED_OFF + 128;
+constexpr int H3_BAR_OFF = H3_RED_OFF + 256;
 constexpr int H3_SMEM = H3_BAR_OFF + 128;
 constexpr uint32_t H3_SET_COLS = 3 * H3_BN;          // 192 TMEM columns per accumulator set (L0, L1, L2)
 
@@ -479,9 +479,30 @@ struct Head3Args {
   float* part_g;
   int parts;                    // m_tiles * p_chunks
   int Cb, m_tiles, p_tiles128, p_tiles, p_chunks, tiles_per_chunk;
+  int prefetch_ahead;           // B tiles pulled into L2 this many tiles ahead of the staged copy (0: none; measured: no effect)
   long long n_items;
 };
 
+// L2 residency hints: the targets are shared by every chain (40.8 MB: L2-resident if the 2.6 GB stream of G does not evict them;
+// the first version re-read them from HBM for every chain: 2.58 GB of DRAM reads per 64-chain batch in ncu)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint(float* p, const float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -505,7 +526,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) head3_kernel(Head3Args a) {
       tc::mbar_init(b_full + s, 1);
       tc::mbar_init(b_empty + s, 1);
       tc::mbar_init(t_full + s, 1);
-      tc::mbar_init(t_empty + s, 8);   // one arrival per epilogue warp
+      tc::mbar_init(t_empty + s, 16);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -536,8 +557,20 @@ __global__ void __launch_bounds__(H3_THREADS, 1) head3_kernel(Head3Args a) {
         expect_tx(a_full, (uint32_t)XTILE);
         bulk_load(At, a.a_img + ((long long)c * a.m_tiles + mt) * XTILE, (uint32_t)XTILE, a_full);
         const int pt_lo = pc * a.tiles_per_chunk, pt_hi = min(pt_lo + a.tiles_per_chunk, a.p_tiles);
+        // Two shared-memory stages cannot hide the latency of a 43 KB tile that comes from HBM (the load of tile t+2 starts when the
+        // MMAs of tile t finish and must land within the 0.7 us the MMAs of tile t+1 take): the tiles are pulled into L2 a few tiles
+        // ahead, so the staged copy is an L2 hit.
+        const int kAhead = a.prefetch_ahead;
+        auto prefetch = [&](int pt) {
+          const unsigned char* src = a.b_img + ((long long)c * a.p_tiles128 + (pt >> 1)) * XTILE + (pt & 1) * H3_BPIECE;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (long long)i * XPIECE), "r"((uint32_t)H3_BPIECE) : "memory");
+        };
+        for (int pt = pt_lo; pt < pt_hi && pt < pt_lo + kAhead; ++pt) prefetch(pt);
         for (int pt = pt_lo; pt < pt_hi; ++pt, ++tcount) {
           const uint32_t st = tcount & 1u;
+          if (pt + kAhead < pt_hi) prefetch(pt + kAhead);
           tc::mbar_wait(b_empty + st, ((tcount >> 1) & 1u) ^ 1u);
           expect_tx(b_full + st, (uint32_t)H3_BTILE);
           unsigned char* dst = smem + H3_B_OFF + st * H3_BTILE;
@@ -571,12 +604,20 @@ __global__ void __launch_bounds__(H3_THREADS, 1) head3_kernel(Head3Args a) {
       }
     }
   } else {             // ---------------- epilogue warps ----------------
-    const int e = warp - 2, q = warp & 3, half = e >> 2;
-    const int et = e * 32 + lane;                    // 0..255
-    const int row1 = q * 32 + lane;                  // phase 1: thread = accumulator row
-    const int c4 = et & 15, rr = et >> 4;            // phase 2: thread = float4 column group c4 of rows rr + 16 i
-    uint32_t it = 0, tcount = 0;
-    for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+    // 16 warps: four per TMEM lane quarter.  Phase 1 (thread = accumulator row, 16 columns): TMEM -> s_a (L0 + (L1 + L2)) -> staging
+    // tile.  Phase 2 (thread = one float4 column group of 4 rows): coalesced rows of the targets in, rows of G out.  The ncu
+    // profile of the first version (8 warps, 880 instructions per thread and tile, IPC 1.4, tensor pipe 26 %) showed the epilogue,
+    // not the tensor core, setting the tile time: per-element masks, 64-bit address arithmetic and the per-element log-likelihood
+    // arithmetic are gone from the inner loops (sums of res and res^2 are accumulated; masks only on edge tiles).
+    const int e = warp - 2, q = warp & 3, colq = e >> 2;
+    const int et = e * 32 + lane;                    // 0..511
+    const int row1 = q * 32 + lane;
+    // (measured and rejected: warp-private staging with no block barrier -- 8 rows x 64 B per store instruction instead of
+    //  2 rows x 256 B: 1.52 ms against 1.33 ms; pulling the B tiles into L2 ahead of the staged copy: no change)
+    const int c4 = et & 15, rr = et >> 4;            // phase 2: float4 column group c4 of rows rr + 32 i
+    uint32_t tcount = 0;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int c, mt, pc;
       decode(item, c, mt, pc);
       const int m0 = mt * 128;
@@ -584,97 +625,128 @@ __global__ void __launch_bounds__(H3_THREADS, 1) head3_kernel(Head3Args a) {
       // its own release protocol: an item of one or two tiles can be overtaken by the producer)
       const float sa_row = __ldg(a.a_sc + ((long long)c * a.m_tiles + mt) * 128 + row1);
       const float bias0 = __ldg(a.bias + (long long)c * a.bias_bs);
-      float ll_acc = 0.0f, g_acc = 0.0f;
+      float s1 = 0.0f, s2 = 0.0f;                    // sums of res and res^2 over this thread's elements
+      int cnt = 0;
       const int pt_lo = pc * a.tiles_per_chunk, pt_hi = min(pt_lo + a.tiles_per_chunk, a.p_tiles);
+      const bool rows_full = m0 + 128 <= a.M;
+      const float* ybase = PREDICT ? nullptr : a.Y + (long long)(m0 + rr) * a.ldy + 4 * c4;
+      float* gbase = a.G + (long long)c * a.g_bs + (long long)(m0 + rr) * a.ldg + 4 * c4;
+      const float* sbbase = a.b_sc + (long long)c * a.p_tiles128 * 128 + 4 * c4;
       for (int pt = pt_lo; pt < pt_hi; ++pt, ++tcount) {
         const uint32_t st = tcount & 1u, use = (tcount >> 1) & 1u;
         const int p0 = pt * H3_BN + 4 * c4;          // this thread's first column
+        const bool full = rows_full && (pt + 1) * H3_BN <= a.P;
         // targets and column scales of this thread's float4s, in flight while the tensor core works
-        float4 yv[8];
+        float4 yv[4];
         float4 sb4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 < a.P) sb4 = __ldg(reinterpret_cast<const float4*>(a.b_sc + (long long)c * a.p_tiles128 * 128 + p0));
+        if (p0 < a.P) sb4 = __ldg(reinterpret_cast<const float4*>(sbbase + pt * H3_BN));
         if (!PREDICT) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = m0 + rr + 16 * i;
-            yv[i] = (m < a.M && p0 < a.P) ? __ldg(reinterpret_cast<const float4*>(a.Y + (long long)m * a.ldy + p0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 4; ++i) {
+            yv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (full || (m0 + rr + 32 * i < a.M && p0 < a.P)) yv[i] = ld_hint(ybase + (long long)(32 * i) * a.ldy + pt * H3_BN, pol_keep);
           }
         }
         tc::mbar_wait(t_full + st, use);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {  // phase 1: TMEM -> s_a (L0 + L1 + L2) -> staging tile, thread = row
-          float* srow = stage + row1 * H3_LD + half * 32;
-          const uint32_t tbase = tmem_d + st * H3_SET_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+        {  // phase 1
+          float* srow = stage + row1 * H3_LD + colq * 16;
+          const uint32_t tbase = tmem_d + st * H3_SET_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(colq * 16);
+          uint32_t l0r[2][8], l1r[2][8], l2r[2][8];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t l0r[2][8], l1r[2][8], l2r[2][8];
+          for (int g2 = 0; g2 < 2; ++g2) {
+            tmem_ld8(tbase + (uint32_t)(g2 * 8), l0r[g2]);
+            tmem_ld8(tbase + (uint32_t)(g2 * 8 + H3_BN), l1r[g2]);
+            tmem_ld8(tbase + (uint32_t)(g2 * 8 + 2 * H3_BN), l2r[g2]);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const unsigned long long sa2 = tc::pk2(sa_row, sa_row);
 #pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-              const uint32_t ta = tbase + (uint32_t)(hh * 16 + g2 * 8);
-              tmem_ld8(ta, l0r[g2]);
-              tmem_ld8(ta + (uint32_t)H3_BN, l1r[g2]);
-              tmem_ld8(ta + 2u * H3_BN, l2r[g2]);
+          for (int g2 = 0; g2 < 2; ++g2) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const unsigned long long low = add2(tc::pk2(__uint_as_float(l1r[g2][j]), __uint_as_float(l1r[g2][j + 1])),
+                                                  tc::pk2(__uint_as_float(l2r[g2][j]), __uint_as_float(l2r[g2][j + 1])));
+              const unsigned long long sum = add2(tc::pk2(__uint_as_float(l0r[g2][j]), __uint_as_float(l0r[g2][j + 1])), low);
+              const unsigned long long sc = mul2(sum, sa2);
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(v[j]), "=f"(v[j + 1]) : "l"(sc));
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = combine3(l0r[g2][j], l1r[g2][j], l2r[g2][j]) * sa_row;
-              *reinterpret_cast<float4*>(srow + hh * 16 + g2 * 8) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(srow + hh * 16 + g2 * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
+            *reinterpret_cast<float4*>(srow + g2 * 8) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(srow + g2 * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty + st);    // the accumulator set may be overwritten
-        named_bar_sync(1, 256);
-        {  // phase 2: coalesced rows, thread = float4 column group
-          const int nv = a.P - p0;                   // valid columns of this thread's float4
+        named_bar_sync(1, 512);
+        {  // phase 2
+          const float* srow = stage + rr * H3_LD + 4 * c4;
+          float* grow = gbase + pt * H3_BN;
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rr + 16 * i, m = m0 + r;
-            if (m < a.M && nv > 0) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + r * H3_LD + 4 * c4);
-              const float o[4] = {fmaf(t.x, sb4.x, bias0), fmaf(t.y, sb4.y, bias0), fmaf(t.z, sb4.z, bias0), fmaf(t.w, sb4.w, bias0)};
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = *reinterpret_cast<const float4*>(srow + 32 * i * H3_LD);
+              const float o0 = fmaf(t.x, sb4.x, bias0), o1 = fmaf(t.y, sb4.y, bias0), o2 = fmaf(t.z, sb4.z, bias0), o3 = fmaf(t.w, sb4.w, bias0);
               if (PREDICT) {
-                float* orow = a.G + (long long)c * a.g_bs + (long long)m * a.ldg + p0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < nv) orow[j] = o[j];
+                float* orow = grow + (long long)(32 * i) * a.ldg;
+                orow[0] = o0; orow[1] = o1; orow[2] = o2; orow[3] = o3;
               } else {
-                const float y[4] = {yv[i].x, yv[i].y, yv[i].z, yv[i].w};
-                float gq[4];
+                const float r0 = o0 - yv[i].x, r1 = o1 - yv[i].y, r2 = o2 - yv[i].z, r3 = o3 - yv[i].w;
+                s1 += (r0 + r1) + (r2 + r3);
+                s2 = fmaf(r0, r0, s2); s2 = fmaf(r1, r1, s2); s2 = fmaf(r2, r2, s2); s2 = fmaf(r3, r3, s2);
+                st_hint(grow + (long long)(32 * i) * a.ldg, make_float4(-a.prec * r0, -a.prec * r1, -a.prec * r2, -a.prec * r3), pol_stream);
+              }
+            }
+            cnt += 16;
+          } else {
+            const int nv = a.P - p0;                   // valid columns of this thread's float4
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  gq[j] = 0.0f;
-                  if (j < nv) {
-                    const float res = o[j] - y[j];
-                    ll_acc += a.ll_const - a.half_prec * res * res;
-                    gq[j] = -a.prec * res;
-                    g_acc += gq[j];
+            for (int i = 0; i < 4; ++i) {
+              const int m = m0 + rr + 32 * i;
+              if (m < a.M && nv > 0) {
+                const float4 t = *reinterpret_cast<const float4*>(srow + 32 * i * H3_LD);
+                const float o[4] = {fmaf(t.x, sb4.x, bias0), fmaf(t.y, sb4.y, bias0), fmaf(t.z, sb4.z, bias0), fmaf(t.w, sb4.w, bias0)};
+                float* orow = grow + (long long)(32 * i) * a.ldg;
+                if (PREDICT) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (j < nv) orow[j] = o[j];
+                } else {
+                  const float y[4] = {yv[i].x, yv[i].y, yv[i].z, yv[i].w};
+                  float gq[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    gq[j] = 0.0f;
+                    if (j < nv) {
+                      const float res = o[j] - y[j];
+                      s1 += res;
+                      s2 = fmaf(res, res, s2);
+                      gq[j] = -a.prec * res;
+                      ++cnt;
+                    }
                   }
+                  *reinterpret_cast<float4*>(orow) = make_float4(gq[0], gq[1], gq[2], gq[3]);
                 }
-                *reinterpret_cast<float4*>(a.G + (long long)c * a.g_bs + (long long)m * a.ldg + p0) = make_float4(gq[0], gq[1], gq[2], gq[3]);
               }
             }
           }
         }
-        named_bar_sync(1, 256);                      // the staging tile is free for the next tile
+        named_bar_sync(1, 512);                      // the staging tile is free for the next tile
       }
-      if (!PREDICT) {   // fixed-order sums of this item's partials
+      if (!PREDICT) {   // fixed-order sums of this item's partials: loglik = n ll_const - half_prec sum res^2, sum G = -prec sum res
+        float ll_acc = fmaf(-a.half_prec, s2, (float)cnt * a.ll_const), g_acc = -a.prec * s1;
         ll_acc = warp_sum(ll_acc);
         g_acc = warp_sum(g_acc);
-        if (lane == 0) { red[e] = ll_acc; red[8 + e] = g_acc; }
-        named_bar_sync(1, 256);
+        if (lane == 0) { red[e] = ll_acc; red[16 + e] = g_acc; }
+        named_bar_sync(1, 512);
         if (et == 0) {
-          float s0 = 0.0f, s1 = 0.0f;
-          for (int w = 0; w < 8; ++w) { s0 += red[w]; s1 += red[8 + w]; }
-          a.part_ll[(long long)c * a.parts + mt * a.p_chunks + pc] = s0;
-          a.part_g[(long long)c * a.parts + mt * a.p_chunks + pc] = s1;
+          float t0 = 0.0f, t1 = 0.0f;
+          for (int w = 0; w < 16; ++w) { t0 += red[w]; t1 += red[16 + w]; }
+          a.part_ll[(long long)c * a.parts + mt * a.p_chunks + pc] = t0;
+          a.part_g[(long long)c * a.parts + mt * a.p_chunks + pc] = t1;
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, 512);
       }
     }
   }

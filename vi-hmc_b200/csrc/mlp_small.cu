@@ -59,7 +59,7 @@ static int fill_params(const vihmc_problem* p, SmallParams& P, int& W, long long
   P.D = p->D; P.d = p->d; P.N = p->N;
   P.tau_out = p->tau_out; P.inv_prior_scale = 1.0f / p->prior_scale;
   P.prior_sigma_scalar = p->prior_sigma_scalar; P.prior_log_norm = p->prior_log_norm;
-  P.x = p->x; P.y = p->y; P.frozen = p->frozen; P.prior_mu = p->prior_mu; P.prior_sigma = p->prior_sigma;
+  P.x = p->x; P.y = p->y; P.frozen = p->frozen; P.frozen_cs = p->frozen_chain_stride; P.prior_mu = p->prior_mu; P.prior_sigma = p->prior_sigma;
   P.sens_ind = reinterpret_cast<const long long*>(p->sens_ind);
   fast = allow_fast && fast_path_enabled() && warps_per_chain_for(C) == 1 && nh == 2 && p->in_a == 1 && p->act == VIHMC_ACT_TANH &&
          p->N <= (32 / W) * 8;
@@ -188,6 +188,9 @@ int mlp_small_sample(const vihmc_problem* prob, const vihmc_sampler_cfg* cfg, lo
   if (io != nullptr) {
     a.A.accepted = io->accepted; a.A.hamiltonians = io->hamiltonians; a.A.logp_out = io->logp; a.A.step_sizes = io->step_sizes;
     a.A.inj_p = io->inject_momenta; a.A.inj_u = io->inject_uniforms;
+    a.A.vi_sigma = io->vi_sigma; a.A.vi_params = io->vi_params; a.A.inj_vi = io->inject_vi_normals;
+    if (io->vi_sigma != nullptr && prob->frozen == nullptr)
+      return fail(VIHMC_ERR_INVALID, "the VI redraw needs the variational means (prob->frozen) and sens_ind");
   }
   return dispatch(W, kOpSample, P, a, st);
 }

@@ -53,6 +53,7 @@ struct SmallParams {
   long long D, d, N;
   float tau_out, inv_prior_scale, prior_sigma_scalar, prior_log_norm;
   const float *x, *y, *frozen, *prior_mu, *prior_sigma;
+  long long frozen_cs;   // chain stride of `frozen` (0: shared by every chain)
   const long long* sens_ind;
   SmallLayout lay;
 };
@@ -318,7 +319,7 @@ __device__ __forceinline__ float stage_chunk(float* sm, const SmallParams& P, in
 // One-time per-chain setup: zero the weight tables, load frozen weights, decode coordinates, load
 // the prior and q (scattered into the tables).  Returns this thread's target when N fits one chunk.
 template <int W, int NW>
-__device__ float chain_init(float* sm, const SmallParams& P, const float* q_row, int ct, int bar) {
+__device__ float chain_init(float* sm, const SmallParams& P, const float* q_row, int ct, int bar, long long chain = 0) {
   using C = Cfg<W, NW>;
   const SmallLayout& L = P.lay;
   for (int i = ct; i < L.w_total; i += C::T) sm[i] = 0.0f;                 // padded units and weight-row padding stay zero
@@ -328,7 +329,7 @@ __device__ float chain_init(float* sm, const SmallParams& P, const float* q_row,
     for (long long f = ct; f < P.D; f += C::T) {
       int wpos, wposT, a, b;
       decode_coord(P, W, f, wpos, wposT, a, b);
-      const float v = __ldg(P.frozen + f);
+      const float v = __ldg(P.frozen + chain * P.frozen_cs + f);
       sm[wpos] = v;
       if (wposT >= 0) sm[wposT] = v;
     }
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_gra
   if (chain >= C) return;
   const SmallLayout& L = P.lay;
   float* sm = smem + (size_t)slot * L.total;
-  const float yv0 = chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar);
+  const float yv0 = chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar, chain);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
   float lp_lane = 0.0f;
   auto consume = [&](int i, float gl) {
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(128) mlp_small_predict_kernel(SmallParams P, l
   const long long chain = (long long)blockIdx.x * (blockDim.x / T) + slot;
   if (chain >= C) return;
   float* sm = smem + (size_t)slot * P.lay.total;
-  chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar);
+  chain_init<W, NW>(sm, P, q + chain * P.d, ct, bar, chain);
   const int n_chunks = (int)((P.N + Cf::NC - 1) / Cf::NC);
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     if (chunk > 0) {
@@ -808,6 +809,9 @@ struct SampleArgs {
   float* step_sizes;
   const float* inj_p;
   const float* inj_u;
+  const float* vi_sigma;   // per-sample VI redraw (vihmc_sampler_io): [D] standard deviations, or null
+  float* vi_params;        // [num_samples, C, D] out, or null
+  const float* inj_vi;     // [num_samples, C, D] injected normals, or null
 };
 
 template <int W, int NW, bool FAST>
@@ -823,7 +827,7 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
   const int d = (int)P.d;
   const long long C = A.C;
   const float* q0 = A.q0 + chain * d;
-  const float yv0 = chain_init<W, NW>(sm, P, q0, ct, bar);
+  const float yv0 = chain_init<W, NW>(sm, P, q0, ct, bar, chain);
   FastRegs F;
   if constexpr (FAST) fast_setup<W>(sm, ct, yv0, F);
   const int* wposv = reinterpret_cast<const int*>(sm + L.wpos);
@@ -845,6 +849,40 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
     if (A.cfg.hamiltorch_fallback_rule && n == burn + 1) {
       for (int i = ct; i < d; i += T) sm[L.qf + i] = q0[i];
       logp_f = logp_init;
+    }
+    // ---- per-sample VI redraw (my_make_func.py:45-50): all D frozen weights = mu + sigma z, then the sampled ones on top ----
+    if (A.vi_sigma != nullptr) {
+      const long long D = P.D;
+      for (long long jb = ct; 4 * jb < D; jb += T) {
+        float zz[4];
+        if (A.inj_vi != nullptr) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) zz[t] = 4 * jb + t < D ? A.inj_vi[((long long)n * C + chain) * D + 4 * jb + t] : 0.0f;
+        } else {
+          const float4 z = philox_normal4(A.cfg.seed, gchain, (uint32_t)n, (uint32_t)jb, STREAM_VI_REDRAW);
+          zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const long long f = 4 * jb + t;
+          if (f < D) {
+            int wpos, wposT, ao, bo;
+            decode_coord(P, W, f, wpos, wposT, ao, bo);
+            const float v = fmaf(__ldg(A.vi_sigma + f), zz[t], __ldg(P.frozen + chain * P.frozen_cs + f));
+            sm[wpos] = v;
+            if (wposT >= 0) sm[wposT] = v;
+            if (A.vi_params != nullptr) A.vi_params[((long long)n * C + chain) * D + f] = v;
+          }
+        }
+      }
+      chain_sync<NW>(bar);
+      for (int i = ct; i < d; i += T) {
+        const float qv = sm[L.q + i];
+        sm[wposv[i]] = qv;
+        const int wt = wposTv[i];
+        if (wt >= 0) sm[wt] = qv;
+      }
+      chain_sync<NW>(bar);
     }
     // ---- momentum ----
     float ke = 0.0f;

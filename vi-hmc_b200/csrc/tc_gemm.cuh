@@ -837,16 +837,16 @@ inline int splitk_chunk() {
   return v;
 }
 #define kSplitKChunk (::vihmc::splitk_chunk())          /* K slice per CTA once K exceeds kSplitKThreshold */
-#define kSplitKThreshold (2 * ::vihmc::splitk_chunk())
+#define kSplitKThreshold (::vihmc::splitk_chunk() + ::vihmc::splitk_chunk() / 2)   /* K = 500 (the M = 2 split closures) -> two slices */
 
 constexpr int kFillSplitMinK = 512;     // medium reductions are split only to put more CTAs on the GPU (few chains)
 constexpr int kFillSplitMax = 8;
 
 // floats of scratch a split-K GEMM of this shape needs (0 if it will not be split)
 inline long long splitk_scratch_floats(int M, int N, int K, int batch) {
-  if (K < kFillSplitMinK) return 0;
-  const int splits = K > kSplitKThreshold ? (K + kSplitKChunk - 1) / kSplitKChunk : kFillSplitMax;
-  return (long long)splits * batch * M * N;
+  if (K > kSplitKThreshold) return (long long)((K + kSplitKChunk - 1) / kSplitKChunk) * batch * M * N;
+  if (K >= kFillSplitMinK) return (long long)kFillSplitMax * batch * M * N;
+  return 0;
 }
 
 // shapes the tensor-core kernel is used for; everything else stays on the FP32-SIMT kernel

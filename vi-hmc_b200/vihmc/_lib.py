@@ -25,7 +25,7 @@ class Problem(C.Structure):
         ("tau_out", C.c_float), ("prior_scale", C.c_float), ("prior_sigma_scalar", C.c_float),
         ("prior_log_norm", C.c_float),
         ("x", C.c_void_p), ("x2", C.c_void_p), ("y", C.c_void_p), ("frozen", C.c_void_p), ("sens_ind", C.c_void_p),
-        ("prior_mu", C.c_void_p), ("prior_sigma", C.c_void_p),
+        ("prior_mu", C.c_void_p), ("prior_sigma", C.c_void_p), ("frozen_chain_stride", C.c_int64),
     ]
 
 
@@ -41,6 +41,7 @@ class SamplerIO(C.Structure):
     _fields_ = [
         ("accepted", C.c_void_p), ("hamiltonians", C.c_void_p), ("logp", C.c_void_p), ("step_sizes", C.c_void_p),
         ("inject_momenta", C.c_void_p), ("inject_uniforms", C.c_void_p),
+        ("vi_sigma", C.c_void_p), ("vi_params", C.c_void_p), ("inject_vi_normals", C.c_void_p),
     ]
 
 

@@ -181,6 +181,7 @@ class SampleResult:
     step_sizes: Optional[torch.Tensor]     # [C]
     grad_evals_per_chain: int = 0
     gpu_launches: int = 0
+    vi_params: Optional[torch.Tensor] = None   # [num_samples, C, D]: the redrawn weight vectors (vi_redraw=True)
 
     @property
     def acceptance_rate(self) -> float:
@@ -191,8 +192,13 @@ def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: 
                 integrator: int = INTEGRATOR_LEAPFROG, adapt_step_size: bool = False, desired_accept_rate: float = 0.8,
                 seed: int = 0, chain_offset: int = 0, hamiltorch_fallback_rule: bool = True, diagnostics: bool = True,
                 inject_momenta: Optional[torch.Tensor] = None, inject_uniforms: Optional[torch.Tensor] = None,
-                to_host: bool = True, force_general: bool = False) -> SampleResult:
+                to_host: bool = True, force_general: bool = False, vi_redraw: bool = False,
+                inject_vi_normals: Optional[torch.Tensor] = None) -> SampleResult:
     """Advance C = q0.shape[0] chains.  specs: one LogProbSpec/Prepared (leapfrog) or several (splitting).
+
+    vi_redraw: the reference's ``sample_weights`` hook once per iteration (Neural_network/VI_HMC/my_make_func.py:45-50): all D
+    frozen weights of every chain are redrawn from N(mu, sigma) (spec.frozen, spec.vi_sigma; Philox stream 2 or
+    ``inject_vi_normals`` [num_samples, C, D]) before the momentum draw; the draws come back as ``vi_params``.
 
     Inputs may be host tensors (they are copied to the GPU here); with ``to_host`` the result tensors are
     copied back, so one call is a complete host-to-host sampling run.
@@ -226,6 +232,19 @@ def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: 
     if inj_u is not None:
         assert tuple(inj_u.shape) == (num_samples, Cn), inj_u.shape
         io.inject_uniforms = inj_u.data_ptr()
+    vip = vsig = inj_v = None
+    if vi_redraw:
+        sp0 = preps[0].spec
+        if sp0.frozen is None or sp0.vi_sigma is None:
+            raise ValueError("vi_redraw needs the VI-HMC split: spec.frozen (means), spec.vi_sigma and spec.sens_ind")
+        Dn = sp0.D
+        vsig = _to_dev(sp0.vi_sigma, dev)
+        vip = torch.empty((num_samples, Cn, Dn), dtype=torch.float32, device=dev)
+        io.vi_sigma, io.vi_params = vsig.data_ptr(), vip.data_ptr()
+        inj_v = _to_dev(inject_vi_normals, dev)
+        if inj_v is not None:
+            assert tuple(inj_v.shape) == (num_samples, Cn, Dn), inj_v.shape
+            io.inject_vi_normals = inj_v.data_ptr()
     M = len(preps)
     evals = num_samples * (num_steps + 1) if integrator == INTEGRATOR_LEAPFROG else num_samples * num_steps * 2 * M
     launches = 0
@@ -247,7 +266,7 @@ def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: 
                                   ws.numel(), _stream(dev))
             launches = -1  # many; counted by the caller from the launch model if needed
         _lib.check(rc)
-    res = SampleResult(samples, acc, ham, lp, eps, grad_evals_per_chain=evals, gpu_launches=launches)
+    res = SampleResult(samples, acc, ham, lp, eps, grad_evals_per_chain=evals, gpu_launches=launches, vi_params=vip)
     if to_host:
         # device -> pinned host buffers (torch's caching host allocator reuses them across calls), all copies queued on the
         # sampler's stream behind the kernel, one synchronisation at the end
@@ -258,7 +277,7 @@ def run_sampler(specs: Sequence, q0: torch.Tensor, num_samples: int, num_steps: 
             h.copy_(t, non_blocking=True)
             return h
         with torch.cuda.device(dev):
-            res = SampleResult(host(samples), host(acc), host(ham), host(lp), host(eps), evals, launches)
+            res = SampleResult(host(samples), host(acc), host(ham), host(lp), host(eps), evals, launches, host(vip))
             torch.cuda.current_stream(dev).synchronize()
     return res
 

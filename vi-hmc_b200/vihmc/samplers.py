@@ -73,8 +73,14 @@ def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, 
            integrator=Integrator.IMPLICIT, metric=Metric.HESSIAN, debug=False, desired_accept_rate=0.8,
            store_on_GPU=True, pass_grad=None, verbose=False, *, num_chains: Optional[int] = None, seed: int = 0,
            chain_offset: int = 0, return_result: bool = False, inject_momenta=None, inject_uniforms=None,
-           hamiltorch_fallback_rule: bool = True, verify_closures: bool = True):
-    """hamiltorch.samplers.sample on the CUDA engine (see module docstring)."""
+           hamiltorch_fallback_rule: bool = True, verify_closures: bool = True, vi_redraw: bool = False,
+           vi_params_uid: Optional[str] = None, inject_vi_normals=None):
+    """hamiltorch.samplers.sample on the CUDA engine (see module docstring).
+
+    vi_redraw=True runs the reference's per-sample VI redraw -- what a sampler does that calls ``log_prob_func(params, True)`` once
+    per sample (main_VI_HMC.py:96-99 -> my_make_func.py:45-50 ``sample_weights``): every frozen weight is redrawn from its
+    variational N(mu, sigma) at the start of each iteration; with ``vi_params_uid`` the draws are written to
+    ``vi_params_<uid>.npy`` as the hook does ([num_samples, D] for one chain, [num_samples, C, D] for C chains)."""
     if sampler == Sampler.RMHMC:
         raise NotImplementedError("RMHMC is not used by the reference and is not on the accelerated path")
     if inv_mass is not None:
@@ -131,7 +137,11 @@ def sample(log_prob_func, params_init, num_samples=10, num_steps_per_sample=10, 
     res = engine.run_sampler(specs, q0, num_samples, num_steps_per_sample, float(step_size), burn=burn, integrator=integ,
                              adapt_step_size=nuts, desired_accept_rate=desired_accept_rate, seed=seed,
                              chain_offset=chain_offset, hamiltorch_fallback_rule=hamiltorch_fallback_rule,
-                             inject_momenta=inject_momenta, inject_uniforms=inject_uniforms, to_host=True)
+                             inject_momenta=inject_momenta, inject_uniforms=inject_uniforms, to_host=True, vi_redraw=vi_redraw,
+                             inject_vi_normals=inject_vi_normals)
+    if vi_redraw and vi_params_uid is not None:
+        vp = res.vi_params[:, 0] if single else res.vi_params
+        np.save(f"vi_params_{vi_params_uid}.npy", vp.clone().detach().cpu())
     if verbose or debug:
         print("Acceptance Rate {:.2f}".format(res.acceptance_rate))
     if return_result:

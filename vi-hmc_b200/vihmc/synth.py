@@ -105,12 +105,19 @@ def deeponet_numpy_forward(arch: DeepONetArch, theta: np.ndarray, x1: np.ndarray
     return xb @ xt.T + theta[0]
 
 
-def burgers_like(arch: DeepONetArch = DeepONetArch(), n_train: int = 1000, n_t: int = 101, n_x: int = 101, seed: int = 0):
+def burgers_like(arch: DeepONetArch = DeepONetArch(), n_train: int = 1000, n_t: int = 101, n_x: int = 101, seed: int = 0,
+                 out_scale: float = 1.0, trunk_scale: float = 1.0):
     """Burgers-SHAPED synthetic operator data (the real .mat is not bundled; Operator_network/Data/data.txt).
 
     branch inputs: n_train draws of a periodic Gaussian random field on ``arch.in_branch`` sensors
     (RBF in sin(pi dx), length-scale 0.2, amplitude 0.1); trunk grid n_t x n_x time-major;
     y = teacher-DeepONet(theta*) + 0.01 N(0,1) with theta* ~ N(0, 0.1^2).
+    out_scale != 1 multiplies the teacher's outputs: theta*'s scalar output bias and the last branch layer (weights and bias)
+    are scaled, so the scaled teacher is still a member of the architecture.  With theta* ~ N(0, 0.1^2) the raw outputs have rms
+    1.3; out_scale = 0.15 puts the targets in the +-0.2 range SURVEY.md 8(d) specifies for the Burgers-shaped data (the bench
+    legs use it).  trunk_scale != 1 scales the last trunk layer the same way (the curvature of the log-posterior along the branch
+    weights grows with the square of the trunk features, so the feature scale decides which leapfrog step sizes are stable).
+    The defaults 1.0 are what the golden vectors were generated with.
     Returns x1 (N,in_branch) f32, x2 (P,2) f32, y (N,P) f32, theta_star (D,) f32.
     """
     rs = np.random.RandomState(seed)
@@ -122,6 +129,21 @@ def burgers_like(arch: DeepONetArch = DeepONetArch(), n_train: int = 1000, n_t: 
     x1 = (chol @ rs.randn(m, n_train)).T
     x2 = trunk_grid(n_t, n_x)
     theta = 0.1 * rs.randn(arch.num_params)
+    if out_scale != 1.0:
+        theta[0] *= out_scale
+        off = 1
+        dims = arch.stack_dims("branch")
+        for o, i in dims[:-1]:
+            off += o * i + o
+        o, i = dims[-1]
+        theta[off:off + o * i + o] *= out_scale
+    if trunk_scale != 1.0:
+        off = 1 + sum(o * i + o for o, i in arch.stack_dims("branch"))
+        dims = arch.stack_dims("trunk")
+        for o, i in dims[:-1]:
+            off += o * i + o
+        o, i = dims[-1]
+        theta[off:off + o * i + o] *= trunk_scale
     y = deeponet_numpy_forward(arch, theta, x1, x2) + 0.01 * rs.randn(n_train, x2.shape[0])
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     return f32(x1), f32(x2), f32(y), f32(theta)
