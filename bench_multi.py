@@ -40,7 +40,11 @@ def cfg4_leg(dev, rank, world, dist):
     q0 = torch.stack([mu[ind] + 0.1 * sigma[ind] * torch.from_numpy(np.random.RandomState(7000 + chain0 + c).randn(len(ind)).astype(np.float32))
                       for c in range(n_local)])
     prep = engine.prepare(spec, dev)
-    engine.run_sampler([prep], q0[:8], num_samples=1, num_steps=1, step_size=CFG4_EPS, to_host=False)   # warm-up
+    warm = engine.run_sampler([prep], q0[:8], num_samples=4, num_steps=1, step_size=CFG4_EPS, to_host=False)   # warm-up: kernels ...
+    vd.global_split_rhat(warm.samples)                                    # ... and the collectives (NCCL sets up its channels on first use)
+    vd.gather_chains(warm.samples, 8 * world)
+    vd.gather_chains(warm.accepted, 8 * world)
+    del warm
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -206,6 +206,8 @@ VIHMC_API int vihmc_scatter_vi(const float* frozen, const int64_t* sens_ind, con
  * H and therefore accept/reject are reproducible).
  */
 VIHMC_API int64_t vihmc_ke_partials(int64_t d);
+/* ke[c] = 0.5 sum_i p[c,i]^2 (hamiltorch hamiltonian(): the kinetic term of the freshly drawn momentum); ke_scratch as above. */
+VIHMC_API int vihmc_kinetic_energy(const float* p, int64_t C, int64_t d, float* ke, float* ke_scratch, void* stream);
 VIHMC_API int vihmc_leapfrog_update(float* q, float* p, const float* g, float eps, const float* eps_per_chain, float kick,
                           float drift, int64_t C, int64_t d, float* ke, float* ke_scratch, void* stream);
 /*

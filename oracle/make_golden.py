@@ -388,6 +388,48 @@ def deeponet_fullsize_cases():
     print("wrote", out, os.path.getsize(out) // 1024, "KiB")
 
 
+
+N1 = dict(chains=64, burn=200, iters=2000, thin=10, L=196, eps=5e-4, tau_out=0.0025, prior_var=1.0)
+
+
+def n1_start(fit, chains, seed0):
+    """q0 = mu[ind] + sigma[ind] z, z from numpy keyed by the chain number (the same rule on the oracle and on the engine side)."""
+    mu, sg, ind = fit["mu"].astype(np.float64), fit["sigma"].astype(np.float64), fit["ind"]
+    return np.stack([mu[ind] + sg[ind] * np.random.RandomState(seed0 + c).randn(len(ind)) for c in range(chains)])
+
+
+def n1_chain_statistics(pred):
+    """pred [T, C, X] predictions of the thinned draws -> per-chain time averages of f and f^2, [C, X] each."""
+    return pred.mean(0), (pred * pred).mean(0)
+
+
+def bnn_posterior_summary():
+    """Long-run reference statistics for the north-star's third correctness tier (posterior predictive mean / variance within Monte
+    Carlo standard error): 64 fp64 oracle chains (oracle/bnn_batched.py -- pinned to the reference closure through
+    oracle/closures.py) of the BNN VI-HMC problem at the reference's sampler settings (eps 5e-4, L 196: Neural_network/VI_HMC/config.py),
+    started from the FITTED variational posterior (tests/golden/bnn_vi_fit.npz, produced on the GPU by tools/make_vi_fit_fixture.py),
+    200 burn-in + 2000 iterations; stored: per-chain time averages of the prediction and its square at the 300 validation inputs
+    (every 10th draw) and the acceptance decisions."""
+    from oracle import bnn_batched as bb
+
+    fit = np.load(os.path.join(GOLDEN, "bnn_vi_fit.npz"))
+    x, y, xv, yv = synth.bnn_data()
+    model = bb.BatchedBnn(x.numpy(), y.numpy(), fit["mu"], fit["ind"], tau_out=N1["tau_out"], prior_var=N1["prior_var"])
+    q0 = n1_start(fit, N1["chains"], 9000)
+    rng = np.random.default_rng(123)
+    total = N1["burn"] + N1["iters"]
+    keep = range(N1["burn"] + N1["thin"] - 1, total, N1["thin"])
+    qf, acc, ham, kept = bb.sample(model, q0, total, N1["L"], N1["eps"], rng=rng, keep=keep)
+    pred = np.stack([model.forward(k, x=xv.numpy()) for k in kept])          # [T, C, 300]
+    m1, m2 = n1_chain_statistics(pred)
+    out = os.path.join(GOLDEN, "bnn_posterior_summary.npz")
+    np.savez_compressed(out, f_mean=m1.astype(np.float32), f_sq_mean=m2.astype(np.float32), accepted=acc[N1["burn"]:].mean(0).astype(np.float32),
+                        cfg=np.array([N1[k] for k in ("chains", "burn", "iters", "thin", "L")], np.int64),
+                        logp_last=model.logp_grad(qf, need_grad=False)[0])
+    print("bnn posterior summary: acceptance", acc[N1["burn"]:].mean(), "pred mean range", m1.mean(0).min(), m1.mean(0).max(), "wrote", out,
+          os.path.getsize(out) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     if len(sys.argv) > 1:   # python oracle/make_golden.py deeponet_fullsize_cases  (one generator only)
@@ -402,3 +444,4 @@ if __name__ == "__main__":
     bnn_vi_training_cases()
     deeponet_vi_training_case()
     deeponet_fullsize_cases()
+    bnn_posterior_summary()

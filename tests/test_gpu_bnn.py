@@ -507,3 +507,58 @@ def test_vi_redraw_philox_stream_and_file(tmp_path, monkeypatch):
     out = samplers.sample(spec, q0[0], num_samples=3, num_steps_per_sample=4, step_size=5e-4, seed=77, vi_redraw=True, vi_params_uid="t1")
     saved = np.load(tmp_path / "vi_params_t1.npy")
     assert saved.shape == (3, 141) and np.array_equal(saved, a.vi_params[:, 0].numpy()) and len(out) == 3
+
+
+def test_long_run_posterior_predictive_matches_oracle_chains():
+    """North-star tier 3 (judge row N1): posterior predictive mean and variance within Monte Carlo standard error over LONG runs.
+    1024 engine chains against the 64 fp64 oracle chains of tests/golden/bnn_posterior_summary.npz (oracle/make_golden.py::
+    bnn_posterior_summary): same problem (BNN VI-HMC, d = 40 of 141), same fitted start law, same sampler settings (eps 5e-4,
+    L 196, 200 burn-in + 2000 iterations, every 10th draw kept).  The chains mix slowly (tools/explore_ess.py: R-hat 2.5 after 150k
+    iterations), so 'same posterior statistics' is tested as 'same law of the chain': the unit of replication is the CHAIN --
+    per-chain time averages of f(x) and f(x)^2 at the 300 validation inputs, compared between the two ensembles with
+    se^2 = var_engine / 1024 + var_oracle / 64.  These and the within-chain predictive variance within 3.5 se at every input (300 inputs x 3 statistics: the
+    expected maximum of 900 unit normals is 3.3), the mean squared z below 1.6, and the acceptance rates within 4 binomial se."""
+    import os
+    import sys
+
+    from vihmc import synth
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import make_golden as mg
+
+    fit = cases.load_golden("bnn_vi_fit.npz")
+    ref = cases.load_golden("bnn_posterior_summary.npz")
+    chains_o, burn, iters, thin, L = (int(v) for v in ref["cfg"])
+    x, y, xv, yv = synth.bnn_data()
+    arch = synth.bnn_arch()
+    numels = arch.tensor_numels()
+    mu, sigma, ind = torch.from_numpy(fit["mu"]), torch.from_numpy(fit["sigma"]), fit["ind"]
+    spec = samplers.define_model_log_prob_bnn(arch, "NLL", x, y, numels, None, [torch.tensor(1.0) for _ in numels], 0.0025,
+                                              params_mu=mu, params_std=sigma, grad_ind=ind)
+    Cg = 1024
+    q0 = torch.from_numpy(mg.n1_start(fit, Cg, 20000).astype(np.float32))
+    kw = dict(to_host=False, hamiltorch_fallback_rule=False)
+    warm = engine.run_sampler([spec], q0, burn, L, 5e-4, burn=burn - 2, seed=5, **kw)
+    res = engine.run_sampler([spec], warm.samples[-1].contiguous(), iters + 1, L, 5e-4, burn=0, seed=6, **kw)
+    draws = res.samples[thin::thin]                                  # states after iterations thin, 2 thin, ... of the timed run
+    assert draws.shape[0] == iters // thin
+    vspec = __import__("dataclasses").replace(spec, x=xv, y=torch.zeros(len(xv), 1))
+    pred = torch.stack([engine.predict(vspec, d_) for d_ in draws]).double()          # [T, C, 300]
+    m1, m2 = pred.mean(0).cpu().numpy(), (pred * pred).mean(0).cpu().numpy()
+    worst, zsq = 0.0, []
+    o1, o2 = ref["f_mean"].astype(np.float64), ref["f_sq_mean"].astype(np.float64)
+    # three chain-level statistics: time average of f, of f^2, and the within-chain predictive variance E_t f^2 - (E_t f)^2
+    for got, want in ((m1, o1), (m2, o2), (m2 - m1 * m1, o2 - o1 * o1)):
+        se = np.sqrt(got.var(0, ddof=1) / Cg + want.var(0, ddof=1) / chains_o)
+        z = (got.mean(0) - want.mean(0)) / se
+        worst = max(worst, float(np.abs(z).max()))
+        zsq.append(float((z * z).mean()))
+    print(f"posterior predictive: max |z| {worst:.2f}, mean z^2 {zsq}")
+    assert worst < 3.5 and max(zsq) < 1.6, (worst, zsq)
+    # pooled predictive variance (between + within chains): 64 oracle chains determine it to ~18 % (sqrt(2 / 63)); a coarse guard
+    var_g = m2.mean(0) - m1.mean(0) ** 2
+    var_o = o2.mean(0) - o1.mean(0) ** 2
+    assert np.median(np.abs(var_g / var_o - 1.0)) < 0.40
+    acc_g = res.accepted[1:].float().mean(0).cpu().numpy()
+    acc_o = ref["accepted"].astype(np.float64)
+    se_a = np.sqrt(acc_g.var(ddof=1) / Cg + acc_o.var(ddof=1) / chains_o)
+    assert abs(acc_g.mean() - acc_o.mean()) < 4 * se_a + 1e-3, (acc_g.mean(), acc_o.mean(), se_a)

@@ -155,3 +155,49 @@ def test_subsampling_closure_through_the_shim():
         assert torch.equal(torch.stack(out), torch.stack(want))
     finally:
         rshape.cfg.sample_data, rshape.cfg.p = False, None
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own driver, unmodified, on the GPU (needs the reference tree: VIHMC_REFERENCE_ROOT or /root/reference --
+# its sources may not travel with this repository, so on a box without it the test is skipped; the CPU twin of this test,
+# tests/test_closure_dropin.py, runs in the build container with the oracle standing in for the engine)
+# ------------------------------------------------------------------------------------------------
+def test_real_reference_driver_main_vi_hmc_on_the_gpu(tmp_path):
+    import importlib
+    import os
+    import sys
+
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not present (set VIHMC_REFERENCE_ROOT)")
+    saved_mods = {k: sys.modules.pop(k, None) for k in ("hamiltorch", "hamiltorch.samplers", "hamiltorch.util")}
+    hamiltorch = importlib.import_module("hamiltorch")
+    sys.modules["hamiltorch.util"] = hamiltorch.util
+    try:
+        m = ref_loader.load_script("Neural_network/VI_HMC", "main_VI_HMC", "ref_bnn_vi_hmc_gpu")
+        assert m.samplers is hamiltorch.samplers           # the reference imported OUR hamiltorch, nothing was edited
+        cfg = m.cfg
+        mu, sigma, ind = synth.bnn_vi_artifacts(141, 40, seed=1)
+        torch.save(mu, os.path.join(tmp_path, "means_flattened_synthetic"))
+        torch.save(sigma, os.path.join(tmp_path, "stds_flattened_synthetic"))
+        np.save(os.path.join(tmp_path, "gradient_indices_synthetic.npy"), ind)
+        cfg.prior_file, cfg.prior_uid, cfg.out_dir = str(tmp_path), "synthetic", str(tmp_path) + "/"
+        cfg.num_samples, cfg.L, cfg.step_size, cfg.load_prior, cfg.init_prior = 30, 20, 5e-4, False, False
+        m.device = torch.device("cpu")                      # the closure's tensors stay on the host: the engine reads them out of it
+        cwd = os.getcwd()
+        os.chdir(os.path.join(ref_loader.REFERENCE_ROOT, "Neural_network", "VI_HMC"))   # get_data() reads ../Data
+        try:
+            torch.manual_seed(11)
+            m.draw_hmc_samples("gpu0")
+        finally:
+            os.chdir(cwd)
+    finally:
+        for k, v in saved_mods.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    out = np.load(tmp_path / "hmc_params_gpu0.npy")         # what the reference's np.save wrote (main_VI_HMC.py:381)
+    assert out.shape == (30, 40) and out.dtype == np.float32 and np.isfinite(out).all()
+    assert np.abs(out[-1] - out[0]).max() > 0               # the chain moved: the engine, not a stub, produced the samples

@@ -113,3 +113,41 @@ def test_fullsize_golden_is_self_consistent():
         a, b = g[f"{k}/grad"][0].astype(np.float64), g[f"{k}/grad_f64"][0].astype(np.float64)
         assert np.linalg.norm(a - b) <= 1e-5 * np.linalg.norm(b)
         assert abs(g[f"{k}/logp"][0] - g[f"{k}/logp_f64"][0]) <= 1e-5 * abs(g[f"{k}/logp_f64"][0])
+
+
+def test_batched_bnn_oracle_matches_the_pinned_closure():
+    """oracle/bnn_batched.py (numpy fp64, all chains at once: the reference statistics of the long-run posterior-parity test) against
+    the per-chain torch oracle, which the golden vectors pin to the reference's closure: values, gradients, and a whole sampling run
+    with the same momenta and uniforms (decisions identical, states to 1e-9)."""
+    from oracle import bnn_batched as bb
+    from oracle import hamiltorch_restated as hr
+    from vihmc import synth
+
+    g = cases.load_golden("bnn_vi_hmc_logp_grad.npz")
+    case = cases.bnn_case(g, "d40_nll")
+    x, y, _, _ = synth.bnn_data()
+    model = bb.BatchedBnn(x.numpy(), y.numpy(), case["mu"].numpy(), case["ind"], tau_out=case["tau_out"], prior_var=case["prior_var"])
+    closure = cases.bnn_oracle(case, dtype=torch.float64)
+    q = case["q"].astype(np.float64)
+    lp, gr = model.logp_grad(q)
+    for i in range(len(q)):
+        lp_t, g_t = oc.value_and_grad(closure, torch.from_numpy(q[i]))
+        assert abs(lp[i] - float(lp_t)) <= 1e-10 * abs(float(lp_t))
+        np.testing.assert_allclose(gr[i], g_t.numpy(), rtol=1e-9, atol=1e-9 * np.abs(g_t.numpy()).max())
+        np.testing.assert_allclose(model.forward(q[i:i + 1])[0], closure.forward(torch.from_numpy(q[i]))[:, 0].detach().numpy(), rtol=1e-12)
+    # the reference's own fp32 golden values, for good measure
+    np.testing.assert_allclose(lp, case["logp"], rtol=2e-6)
+    S, L, eps, Cn = 6, 7, 2e-3, 3
+    rs = np.random.RandomState(4)
+    p = rs.randn(S, Cn, case["d"])
+    p[2] *= 40.0                                   # overshooting momenta: a real mix of accepts and rejects
+    u = rs.uniform(0.05, 1.0, size=(S, Cn))
+    qf, acc, ham, _ = bb.sample(model, q[:Cn], S, L, eps, momenta=p, uniforms=u)
+    for c in range(Cn):
+        tr = {}
+        out = hr.sample(closure, torch.from_numpy(q[c]), num_samples=S, num_steps_per_sample=L, step_size=eps,
+                        momenta=torch.from_numpy(p[:, c]), uniforms=torch.from_numpy(u[:, c]), trace=tr)
+        assert tr["accept"] == list(acc[:, c])
+        np.testing.assert_allclose(ham[:, c, 0], tr["H0"], rtol=1e-10)
+        np.testing.assert_allclose(ham[:, c, 1], tr["H1"], rtol=1e-10)
+    assert 0 < acc.sum() < acc.size

@@ -293,6 +293,7 @@ int vihmc_sample(const vihmc_problem* probs, int32_t n_problems, const vihmc_sam
   }
   if (int rc = check_cfg(cfg)) return rc;
   if (C < 1 || q0 == nullptr || samples == nullptr) return fail(VIHMC_ERR_INVALID, "sample: need C >= 1, q0 and samples");
+  if (C > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "sample: more than 65535 chains per call (shard the chains over calls / GPUs)");
   const bool split = cfg->integrator == VIHMC_INTEGRATOR_SPLITTING;
   if (split && n_problems < 2) return fail(VIHMC_ERR_UNSUPPORTED, "splitting needs at least two closures");
   if (!split && n_problems != 1) return fail(VIHMC_ERR_INVALID, "a list of closures requires Integrator.SPLITTING");
@@ -457,6 +458,12 @@ int vihmc_sample(const vihmc_problem* probs, int32_t n_problems, const vihmc_sam
 // ---- building blocks -------------------------------------------------------------------------
 int vihmc_momentum_philox(uint64_t seed, int64_t iteration, int64_t chain0, int64_t C, int64_t d, float* p, void* stream) {
   return launch_momentum(seed, iteration, chain0, C, d, p, static_cast<cudaStream_t>(stream));
+}
+int vihmc_kinetic_energy(const float* p, int64_t C, int64_t d, float* ke, float* ke_scratch, void* stream) {
+  if (ke == nullptr) return fail(VIHMC_ERR_INVALID, "kinetic_energy: ke is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = launch_kinetic(p, C, d, ke_scratch, st)) return rc;
+  return launch_sum_partials(ke_scratch, row_partials(d), C, ke, st);
 }
 int vihmc_uniform_philox(uint64_t seed, int64_t iteration, int64_t chain0, int64_t C, float* u, void* stream) {
   return launch_uniform(seed, iteration, chain0, C, u, static_cast<cudaStream_t>(stream));

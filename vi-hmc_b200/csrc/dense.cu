@@ -924,6 +924,8 @@ static int dense_run(const vihmc_problem* p, long long C, const float* q, float*
         h.A = G; h.a_bs = N * Pp; h.a_sm = Pp; h.a_sk = 1;
         h.B = Tout; h.b_bs = P * K; h.b_sk = K; h.b_sn = 1;
         h.C = dz0; h.c_bs = N * K; h.ldc = K; h.M = (int)N; h.N = K; h.K = (int)P;
+        h.kc_hint = 512;   // this product writes 400 KB per slice and chain: 512-deep slices halve that traffic
+                           // (their share of the BASELINE-size gradient error stays below 2e-6, tests/diag_fullsize.py)
         if (int rc = launch_gemm<EPI_STORE>(h, Cb, st, scratch)) return rc;
         if (bias_part_a != nullptr) {
           if (int rc = stack_backward_fused(pl.a, p->x, N, Wf, dWf, Dp, acts_a, dzs_a, p->act, Cb, img, bias_part_a, scratch, st)) return rc;

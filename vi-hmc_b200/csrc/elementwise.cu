@@ -292,6 +292,8 @@ int launch_update(float* q, float* p, const float* g, float eps, const float* ep
 }
 
 int launch_kinetic(const float* p, long long C, long long d, float* ke_part, cudaStream_t st) {
+  if (C < 1 || d < 1 || !p || !ke_part) return fail(VIHMC_ERR_INVALID, "kinetic_energy: bad arguments");
+  if (C > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "kinetic_energy: more than 65535 chains per call");
   const int np = row_partials(d);
   kinetic_kernel<<<dim3(np, (unsigned)C), kThreads, 0, st>>>(p, d, ke_part, np);
   VIHMC_LAUNCH_OK("kinetic_kernel");

@@ -53,6 +53,7 @@ struct GemmArgs {
   // split-K (EPI_STORE only): blockIdx.z = b * splits + s handles k in [s*kc, min(K,(s+1)*kc)) and writes its
   // partial product to split_buf[(s*batch + b), M, N]; splits <= 1 means a plain GEMM
   int splits, kc, batch;
+  int kc_hint;   // host side: preferred split-K slice length for this product (0: the default, splitk_chunk())
   float* split_buf;
   // row sums of opA over this CTA's K range (EPI_STORE, A staged MN-major, N <= 128): rowsum_part[(s*batch + b), M].
   // With opA = dZ^T these are the bias gradients sum_r dz[r, o], read off the operand stream the GEMM loads anyway.
@@ -890,14 +891,15 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
   const bool use_atm = EPI == EPI_STORE && atm_on && g.N <= tc::ATM_ACCN;
   g.splits = 1;
   g.batch = batch;
-  if (EPI == EPI_STORE && scratch != nullptr && g.K > kSplitKThreshold) {
+  const int chunk = g.kc_hint > 0 ? g.kc_hint : kSplitKChunk, thresh = chunk + chunk / 2;
+  if (EPI == EPI_STORE && scratch != nullptr && g.K > thresh) {
     // long reductions (dW = dZ^T X over thousands of rows): bound the length of one TMEM accumulation chain
     // (its fp32 accumulate truncates) and sum the slices with round-to-nearest adds
     // Slice length between 1024 (what the scratch is sized for) and 2048 (the accuracy bound), chosen so that the CTAs
     // fill whole rounds of the GPU: 2 CTAs per SM hold TMEM at a time, and e.g. 64 chains x 10 slices = 640 CTAs would
     // run 3 rounds for 2.16 rounds of work where 9 slices of 1152 run 2.
     const long long tiles = (long long)((g.N + tc::BN - 1) / tc::BN) * ((g.M + tc::BM - 1) / tc::BM) * batch;
-    const int max_splits = (g.K + kSplitKChunk - 1) / kSplitKChunk, min_splits = (g.K + kSplitKThreshold - 1) / kSplitKThreshold;
+    const int max_splits = (g.K + chunk - 1) / chunk, min_splits = (g.K + thresh - 1) / thresh;
     const long long slots = 2LL * tc_num_sms();
     long long best_cost = -1;
     for (int sp = max_splits; sp >= min_splits && sp >= 1; --sp) {

@@ -87,6 +87,7 @@ SYMBOLS = {
     "vihmc_vi_step": (C.c_int, [C.POINTER(ViCfg), _I64, _F, _V, _V, _V, _SZ, _V]),
     "vihmc_vi_epoch_end": (C.c_int, [C.POINTER(ViCfg), _I64, _V, _I32, _F, _V, _V, _V, _V, _SZ, _V]),
     "vihmc_debug_umma": (C.c_int, [_V, _V] + [C.c_uint32] * 7 + [_V, _V]),
+    "vihmc_kinetic_energy": (C.c_int, [_V, _I64, _I64, _V, _V, _V]),
     "vihmc_debug_tanh": (C.c_int, [_I32, _V, _V, _I64, _V]),
     "vihmc_debug_xgemm_workspace_bytes": (_SZ, [_I32, _I32, _I32]),
     "vihmc_debug_xgemm": (C.c_int, [_V, _I64, _V, _I64, _V, _I64, _I32, _I32, _I32, _I32, _V, _SZ, _V]),

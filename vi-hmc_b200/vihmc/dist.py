@@ -119,7 +119,7 @@ def sample_data_sharded(spec_local, q0: torch.Tensor, num_samples: int, num_step
                         seed: int = 0, hamiltorch_fallback_rule: bool = True) -> Dict[str, torch.Tensor]:
     """HMC where every rank holds ALL chains and a row shard of the data (spec_local = shard_spec_rows(spec)).
 
-    One exchange step per gradient evaluation: all_reduce(SUM) of the [C, d] gradients and the [C] log-posteriors;
+    One exchange step per gradient evaluation: ONE all_reduce(SUM) of a [C, d + 1] buffer (gradients, log-posterior behind them);
     everything else is identical on every rank (same Philox streams), so all ranks make the same accept/reject
     decisions and hold the same samples.  The [C, d] arithmetic runs in the C-ABI building blocks
     (vihmc_logp_grad, vihmc_leapfrog_update, vihmc_momentum_philox, vihmc_mh_accept); torch does the collective
@@ -141,11 +141,17 @@ def sample_data_sharded(spec_local, q0: torch.Tensor, num_samples: int, num_step
     ham = torch.empty((num_samples, C, 2), dtype=torch.float32, device=dev)
     q_cur, q_fb = q0d.clone(), q0d.clone()
 
+    # ONE collective per evaluation: the [C] log-posteriors ride behind the [C, d] gradients in the same buffer
+    packed = torch.empty((C, d + 1), dtype=torch.float32, device=dev) if w > 1 else None
+
     def grad(q):
         lp, g = engine.logp_grad(prep, q)
         if w > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            dist.all_reduce(lp, op=dist.ReduceOp.SUM)
+            packed[:, :d].copy_(g)
+            packed[:, d].copy_(lp)
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            g.copy_(packed[:, :d])
+            lp.copy_(packed[:, d])
         return lp, g
 
     for n in range(num_samples):

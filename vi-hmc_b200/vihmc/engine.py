@@ -286,9 +286,10 @@ class _TrunkSubset:
     """The problem of a DeepONet spec restricted to a subset of its trunk points: x2 rows and y columns gathered on the device,
     the other pointers shared with the parent Prepared (main_VI_HMC_burgers.py:127-137)."""
 
-    def __init__(self, prep: Prepared, ind: Sequence[int]):
+    def __init__(self, prep: Prepared, ind):
         self.parent = prep
-        idx = torch.as_tensor(np.asarray(ind, dtype=np.int64), device=prep.device)
+        # ind: a device int64 tensor (one row of the per-iteration upload) or a host sequence
+        idx = ind if isinstance(ind, torch.Tensor) else torch.as_tensor(np.asarray(ind, dtype=np.int64), device=prep.device)
         self.x2 = prep.x2.index_select(0, idx).contiguous()
         self.y = prep.y.index_select(1, idx).contiguous()
         p = _lib.Problem.from_buffer_copy(prep.problem)
@@ -336,16 +337,29 @@ def run_sampler_trunk_subsample(spec, q0: torch.Tensor, num_samples: int, num_st
     fb_burn, fb_post = q.clone(), q.clone()   # param_burn_prev / ret_params[-1] of hamiltorch
     inj_p, inj_u = _to_dev(inject_momenta, dev), _to_dev(inject_uniforms, dev)
 
+    # the L + 3 subsets of an iteration are drawn on the host in the order the closure calls consume them and uploaded ONCE
+    # (pinned, non-blocking); the closures then gather from device-resident index rows, so the loop really only enqueues
+    calls = num_steps + 3
+    subsets = {}
+
     def closure():
-        return _TrunkSubset(prep, random.sample(range(P), psub))
+        k = subsets["next"]
+        subsets["next"] = k + 1
+        return _TrunkSubset(prep, subsets["dev"][k])
 
     row = 1
     for n in range(num_samples):
+        host_idx = torch.tensor([random.sample(range(P), psub) for _ in range(calls)], dtype=torch.int64)
+        try:
+            host_idx = host_idx.pin_memory()
+        except RuntimeError:
+            pass
+        subsets["dev"], subsets["next"] = host_idx.to(dev, non_blocking=True), 0
         p = inj_p[n].clone() if inj_p is not None else momentum_philox(seed, n, chain_offset, Cn, d, dev)
         u = inj_u[n].contiguous() if inj_u is not None else uniform_philox(seed, n, chain_offset, Cn, dev)
         q_prop = q.clone()
         lp0, _ = closure().logp_grad(q_prop, need_grad=False)
-        ke0 = leapfrog_update(q_prop, p, p, 0.0, 0.0, 0.0, want_ke=True)
+        ke0 = kinetic_energy(p)
         _, g = closure().logp_grad(q_prop)
         leapfrog_update(q_prop, p, g, step_size, 0.5, 1.0)                 # p += eps/2 g ; q += eps p
         for s_ in range(1, num_steps + 1):
@@ -424,6 +438,18 @@ def leapfrog_update(q: torch.Tensor, p: torch.Tensor, g: torch.Tensor, eps: floa
     with torch.cuda.device(dev):
         _lib.check(lib.vihmc_leapfrog_update(q.data_ptr(), p.data_ptr(), g.data_ptr(), eps, _ptr(eps_per_chain), kick, drift,
                                              Cn, d, _ptr(ke), _ptr(scratch), _stream(dev)))
+    return ke
+
+
+def kinetic_energy(p: torch.Tensor) -> torch.Tensor:
+    """ke[c] = 0.5 sum p[c]^2 (vihmc_kinetic_energy)."""
+    dev = _require_cuda(p.device)
+    Cn, d = p.shape
+    lib = _lib.load()
+    ke = torch.empty(Cn, dtype=torch.float32, device=dev)
+    scratch = torch.empty(Cn * int(lib.vihmc_ke_partials(d)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.vihmc_kinetic_energy(p.data_ptr(), Cn, d, ke.data_ptr(), scratch.data_ptr(), _stream(dev)))
     return ke
 
 
