@@ -31,6 +31,7 @@ bool mlp_small_supported(const vihmc_problem* p) {
 
 static int warps_per_chain_for(long long C);
 static bool fast_path_enabled();
+static int fast_version();
 
 // allow_fast: the caller's kernel has a specialised variant (log-posterior/gradient and the sampler; not predict)
 static int fill_params(const vihmc_problem* p, SmallParams& P, int& W, long long C, bool allow_fast, int& fast) {
@@ -63,6 +64,7 @@ static int fill_params(const vihmc_problem* p, SmallParams& P, int& W, long long
   P.sens_ind = reinterpret_cast<const long long*>(p->sens_ind);
   fast = allow_fast && fast_path_enabled() && warps_per_chain_for(C) == 1 && nh == 2 && p->in_a == 1 && p->act == VIHMC_ACT_TANH &&
          p->N <= (32 / W) * 8;
+  if (fast && W <= 16 && p->last_bias) fast = fast_version();
   P.lay = make_layout(W, nh, p->in_a, p->d, fast != 0);
   return VIHMC_OK;
 }
@@ -92,6 +94,15 @@ static bool fast_path_enabled() {
     return !(e != nullptr && e[0] == '1');
   }();
   return on;
+}
+
+// VIHMC_SMALL_FAST=1 keeps the round-1 specialised evaluation (eval_fast); default: version 2 (eval_fast2) for widths <= 16
+static int fast_version() {
+  static const int v = []() {
+    const char* e = getenv("VIHMC_SMALL_FAST");
+    return (e != nullptr && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
 }
 
 static void pick_geometry(const SmallParams& P, long long C, SmallLaunch& a) {

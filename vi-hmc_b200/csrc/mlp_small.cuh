@@ -30,6 +30,9 @@ constexpr int kMaxHidden = 4;
 #ifndef VIHMC_SMALL_MINBLOCKS
 #define VIHMC_SMALL_MINBLOCKS 4   // register budget of the small-MLP kernels: 65536 / (128 * minblocks) = 128
 #endif
+#ifndef VIHMC_SMALL_MINBLOCKS2
+#define VIHMC_SMALL_MINBLOCKS2 2  // eval_fast2 keeps 2 W activation quads in registers: 255 registers per thread
+#endif
 
 struct SmallLayout {
   // Per-chain shared memory, in floats from the chain base: [weight tables | activation rows | per-coordinate state].
@@ -44,6 +47,7 @@ struct SmallLayout {
   int NC, NCS;
   // per-coordinate state, each dp entries
   int coord_base, dp, q, p, g, qf, pmu, piv, meta, wpos, wposT, red;
+  int part, pmeta;   // specialised path v2: per-lane partial gradient sums [2W+9 slots][33] and each coordinate's offset into them
   int total;
 };
 
@@ -105,6 +109,8 @@ __host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int i
   L.wpos = off; off += L.dp;
   L.wposT = off; off += L.dp;
   L.red = off; off += 8;      // cross-warp reduction slots (two warps per chain)
+  L.pmeta = off; off += fast ? L.dp : 0;
+  L.part = off; off += fast ? (2 * W + 9) * 33 + 3 : 0;
   L.total = off;
   return L;
 }
@@ -527,6 +533,7 @@ __device__ __forceinline__ float eval_likelihood_grad(float* sm, const SmallPara
 struct FastRegs {
   float x[4];   // the lane's 4 inputs (unit mode)
   float yv;     // the lane's target (point mode)
+  float y4[4];  // the targets of the lane's 4 points (version 2: every lane of a point quad forms the residual)
 };
 
 // Unit-mode lane geometry of the specialised path: lane = (unit pair jp, point quad nq), i.e. a 2 x 4 register tile.
@@ -547,6 +554,8 @@ __device__ __forceinline__ void fast_setup(const float* sm, int ct, float yv0, F
   const FastLane<W> ln(ct);
   load8(sm + L.act_base + L.xs + ln.n0, F.x);
   F.yv = yv0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) F.y4[t] = __shfl_sync(0xffffffffu, yv0, (ln.n0 + t) & 31);   // lane n holds the target of point n
 }
 
 // acc[u][t] += sum_k wrow_u[k] * rows[k][t], u < 2, t < 4, on packed pairs; k ascending as in dot_rows.
@@ -693,11 +702,230 @@ __device__ __forceinline__ float eval_fast(float* sm, const SmallParams& P, cons
   return ll_lane;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Specialised evaluation, version 2 (round 2).  ncu of version 1: shared-memory wavefronts 78 % of the pipe's peak, 303 per
+// evaluation -- 128 in the two contractions, ~100 in phase B (lane = coordinate re-reading two 20-point rows per coordinate) and the
+// row stores that only phase B needs, ~35 in the output layer (lane = data point).  Version 2 keeps the lane geometry of the
+// contractions (2 units x 4 points per lane) and removes the other two:
+//   * the activation / gradient quads a lane loads for a contraction STAY in registers, so the lane forms the partial sums of every
+//     weight gradient of its two units over its four points in registers (dW1[j][k] += dz1[j][t] h0[k][t], ...): 2W + 9 values;
+//   * those go to shared memory once (slot-major, stride 33: conflict-free scalar stores), and the owner lane of a sampled coordinate
+//     adds the NQ partials of its coordinate in fixed order (NQ scalar loads instead of two rows);
+//   * the output layer is a sum over the JP lanes of a point quad, done with shuffles in fixed order (every lane of the quad gets
+//     the same value), so h1 and dz0 are never stored.
+// Same operations per element, different summation order than the generic path: equal to rounding, not bit-identical.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ int fast2_slot_count() { return 2 * W + 9; }
+
+// offset of coordinate f's partial sums: slot * 33 + jp (the partials of lanes jp + JP nq, nq < NQ, are JP floats apart)
+__device__ __forceinline__ int fast2_poff(const SmallParams& P, int W, long long f) {
+  const int JP = W / 2, w0 = P.widths[0], w1 = P.widths[1];
+  int slot, j;
+  if (f < w0) { j = (int)f; slot = 2 * W + 2; }                                   // W0[j][0]
+  else if (f < 2 * w0) { j = (int)f - w0; slot = 2 * W + 4; }                     // b0[j]
+  else if (f < 2 * w0 + (long long)w1 * w0) {                                     // W1[j][k]
+    const int r = (int)f - 2 * w0;
+    j = r / w0;
+    return ((j / JP) * W + r % w0) * 33 + j % JP;
+  }
+  else if (f < 2 * w0 + (long long)w1 * w0 + w1) { j = (int)f - 2 * w0 - w1 * w0; slot = 2 * W; }        // b1[j]
+  else if (f < 2 * w0 + (long long)w1 * w0 + 2 * w1) { j = (int)f - 2 * w0 - w1 * w0 - w1; slot = 2 * W + 6; }   // W2[0][j]
+  else return (2 * W + 8) * 33;                                                   // b2
+  return (slot + j / JP) * 33 + j % JP;
+}
+
+template <int W>
+__device__ __forceinline__ void fast2_setup(float* sm, const SmallParams& P, int ct) {
+  const SmallLayout& L = P.lay;
+  int* pm = reinterpret_cast<int*>(sm + L.pmeta);
+  for (int i = ct; i < (int)P.d; i += 32) pm[i] = fast2_poff(P, W, P.sens_ind ? __ldg(P.sens_ind + i) : (long long)i);
+  __syncwarp();
+}
+
+// acc[u][t] += sum_k wrow_u[k] * rows[k][t] as dot_rows_2x4, and the loaded quads rows[k][n0 .. n0+3] are handed back in keep[k]
+template <int W, int NCS>
+__device__ __forceinline__ void dot_rows_2x4_keep(const float* wrows, const float* rows, float (&acc)[2][4], ulonglong2 (&keep)[W]) {
+  constexpr int WSW = (W + 3) / 4 * 4;
+  float w[2][WSW];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int k4 = 0; k4 < WSW / 4; ++k4) {
+      const float4 v = reinterpret_cast<const float4*>(wrows + u * (W / 2) * WSW)[k4];
+      w[u][4 * k4] = v.x; w[u][4 * k4 + 1] = v.y; w[u][4 * k4 + 2] = v.z; w[u][4 * k4 + 3] = v.w;
+    }
+  unsigned long long a[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    a[u][0] = pack2(acc[u][0], acc[u][1]);
+    a[u][1] = pack2(acc[u][2], acc[u][3]);
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(rows + k * NCS);
+    keep[k] = r;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long ww = pack2(w[u][k], w[u][k]);
+      a[u][0] = ffma2(ww, r.x, a[u][0]);
+      a[u][1] = ffma2(ww, r.y, a[u][1]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    unpack2(a[u][0], acc[u][0], acc[u][1]);
+    unpack2(a[u][1], acc[u][2], acc[u][3]);
+  }
+}
+
+// sum over the 4 points of a quad: a . b with a, b packed as (01, 23)
+__device__ __forceinline__ float quad_dot(unsigned long long a01, unsigned long long a23, unsigned long long b01, unsigned long long b23) {
+  unsigned long long p;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(a01), "l"(b01));
+  p = ffma2(a23, b23, p);
+  float lo, hi;
+  unpack2(p, lo, hi);
+  return lo + hi;
+}
+
+template <int W, typename Consume>
+__device__ __forceinline__ float eval_fast2(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F,
+                                            Consume&& consume) {
+  constexpr SmallLayout L0c = make_layout(W, 2, 1, 0, true);   // weight / activation offsets do not depend on d
+  constexpr int NC = L0c.NC, NCS = L0c.NCS, WSW = round_up(W, 4), JP = W / 2, NQ = NC / 4;
+  const SmallLayout& L = P.lay;
+  float* act = sm + L0c.act_base;
+  const FastLane<W> ln(ct);
+  const int j0 = ln.j0, n0 = ln.n0;
+  float h0[2][4], h1[2][4];
+  {  // layer 0: Linear(1, W)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float w = sm[L0c.wbase[0] + (j0 + u * JP) * L0c.ws[0]], b = sm[L0c.bbase[0] + j0 + u * JP];
+      const unsigned long long w2 = pack_f2(w, w), b2 = pack_f2(b, b);
+      unpack_f2(tanh_sel2(fma_f2(w2, pack_f2(F.x[0], F.x[1]), b2)), h0[u][0], h0[u][1]);
+      unpack_f2(tanh_sel2(fma_f2(w2, pack_f2(F.x[2], F.x[3]), b2)), h0[u][2], h0[u][3]);
+      if (ln.unit) store8(act + L0c.h + (j0 + u * JP) * NCS + n0, h0[u]);
+    }
+  }
+  __syncwarp();
+  ulonglong2 hk[W];   // h0[k][n0 .. n0+3] for every k: the operand of the weight-gradient partial sums
+  {  // layer 1: Linear(W, W)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float b = sm[L0c.bbase[1] + j0 + u * JP];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h1[u][t] = b;
+    }
+    dot_rows_2x4_keep<W, NCS>(sm + L0c.wbase[1] + j0 * WSW, act + L0c.h + n0, h1, hk);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      unpack_f2(tanh_sel2(pack_f2(h1[u][0], h1[u][1])), h1[u][0], h1[u][1]);
+      unpack_f2(tanh_sel2(pack_f2(h1[u][2], h1[u][3])), h1[u][2], h1[u][3]);
+    }
+  }
+  // output layer: o[t] = b2 + sum over the JP lanes of this point quad (lanes nq*JP .. nq*JP + JP-1) of w2[j] h1[j][t], fixed order
+  float wo[2], dO[4];
+  float ll_lane = 0.0f;
+  {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) wo[u] = sm[L0c.wbase[2] + j0 + u * JP];
+    float part[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) part[t] = ln.unit ? fmaf(wo[1], h1[1][t], wo[0] * h1[0][t]) : 0.0f;
+    const int base = (ct / JP) * JP;
+    float o[4];
+    const float b2 = sm[L0c.bbase[2]];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = b2;
+#pragma unroll
+    for (int m = 0; m < JP; ++m)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) o[t] += __shfl_sync(0xffffffffu, part[t], (base + m) & 31);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const bool valid = ln.unit && n0 + t < (int)P.N;
+      const float r = o[t] - F.y4[t];
+      dO[t] = valid ? -lik.prec * r : 0.0f;
+      if (valid && j0 == 0) ll_lane += lik.ll_const - lik.half_prec * r * r;
+    }
+  }
+  float dz1[2][4], dz0[2][4];
+  {  // backward through the output layer and the second tanh; dz1 rows are the operand of the backward contraction
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long one = pack_f2(1.0f, 1.0f), wo2 = pack_f2(wo[u], wo[u]);
+#pragma unroll
+      for (int t = 0; t < 4; t += 2) {
+        const unsigned long long h = pack_f2(h1[u][t], h1[u][t + 1]), nh = pack_f2(-h1[u][t], -h1[u][t + 1]);
+        unsigned long long p, q;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(wo2), "l"(pack_f2(dO[t], dO[t + 1])));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(p), "l"(fma_f2(nh, h, one)));
+        unpack_f2(q, dz1[u][t], dz1[u][t + 1]);
+      }
+      if (ln.unit) store8(act + L0c.dz + (W + j0 + u * JP) * NCS + n0, dz1[u]);
+    }
+  }
+  __syncwarp();
+  {  // backward through Linear(W, W) (transposed table) and the first tanh
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dz0[u][t] = 0.0f;
+    ulonglong2 zk[W];   // not needed afterwards; the compiler drops it
+    dot_rows_2x4_keep<W, NCS>(sm + L0c.tbase[1] + j0 * WSW, act + L0c.dz + W * NCS + n0, dz0, zk);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long one = pack_f2(1.0f, 1.0f);
+#pragma unroll
+      for (int t = 0; t < 4; t += 2) {
+        const unsigned long long h = pack_f2(h0[u][t], h0[u][t + 1]), nh = pack_f2(-h0[u][t], -h0[u][t + 1]);
+        unsigned long long q;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(pack_f2(dz0[u][t], dz0[u][t + 1])), "l"(fma_f2(nh, h, one)));
+        unpack_f2(q, dz0[u][t], dz0[u][t + 1]);
+      }
+    }
+  }
+  {  // partial sums of the weight gradients over this lane's four points -> part[slot][lane]
+    float* pt = sm + L.part + ct;
+    const unsigned long long x01 = pack_f2(F.x[0], F.x[1]), x23 = pack_f2(F.x[2], F.x[3]);
+    const unsigned long long d01 = pack_f2(dO[0], dO[1]), d23 = pack_f2(dO[2], dO[3]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long z01 = pack_f2(dz1[u][0], dz1[u][1]), z23 = pack_f2(dz1[u][2], dz1[u][3]);
+      const unsigned long long y01 = pack_f2(dz0[u][0], dz0[u][1]), y23 = pack_f2(dz0[u][2], dz0[u][3]);
+#pragma unroll
+      for (int k = 0; k < W; ++k) pt[(u * W + k) * 33] = quad_dot(z01, z23, hk[k].x, hk[k].y);
+      pt[(2 * W + u) * 33] = (dz1[u][0] + dz1[u][1]) + (dz1[u][2] + dz1[u][3]);
+      pt[(2 * W + 2 + u) * 33] = quad_dot(y01, y23, x01, x23);
+      pt[(2 * W + 4 + u) * 33] = (dz0[u][0] + dz0[u][1]) + (dz0[u][2] + dz0[u][3]);
+      pt[(2 * W + 6 + u) * 33] = quad_dot(d01, d23, pack_f2(h1[u][0], h1[u][1]), pack_f2(h1[u][2], h1[u][3]));
+    }
+    pt[(2 * W + 8) * 33] = (dO[0] + dO[1]) + (dO[2] + dO[3]);
+  }
+  __syncwarp();
+  {  // owner lane of a sampled coordinate: the NQ partials of its coordinate, fixed order
+    const int* pm = reinterpret_cast<const int*>(sm + L.pmeta);
+    const float* part = sm + L.part;
+    for (int i = ct; i < (int)P.d; i += 32) {
+      const float* pp = part + pm[i];
+      float gsum = pp[0];
+#pragma unroll
+      for (int nq = 1; nq < NQ; ++nq) gsum += pp[nq * JP];
+      consume(i, gsum);
+    }
+  }
+  __syncwarp();
+  return ll_lane;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel 1: log-posterior value + gradient for C chains (vihmc_logp_grad, MLP small path)
 // ------------------------------------------------------------------------------------------------
-template <int W, int NW, bool FAST>
-__global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C,
+template <int W, int NW, int FAST>
+__global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C,
                                                                                          const float* __restrict__ q,
                                                                                          float* __restrict__ logp,
                                                                                          float* __restrict__ grad) {
@@ -717,7 +945,12 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_logp_gra
     if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, gl);
   };
   float ll_lane;
-  if constexpr (FAST) {
+  if constexpr (FAST == 2) {
+    FastRegs F;
+    fast_setup<W>(sm, ct, yv0, F);
+    fast2_setup<W>(sm, P, ct);
+    ll_lane = eval_fast2<W>(sm, P, lik, ct, F, consume);
+  } else if constexpr (FAST == 1) {
     FastRegs F;
     fast_setup<W>(sm, ct, yv0, F);
     ll_lane = eval_fast<W>(sm, P, lik, ct, F, consume);
@@ -814,8 +1047,8 @@ struct SampleArgs {
   const float* inj_vi;     // [num_samples, C, D] injected normals, or null
 };
 
-template <int W, int NW, bool FAST>
-__global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
+template <int W, int NW, int FAST>
+__global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr int T = Cfg<W, NW>::T;
   const int ct = threadIdx.x % T, slot = threadIdx.x / T, bar = 1 + slot;
@@ -829,7 +1062,8 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
   const float* q0 = A.q0 + chain * d;
   const float yv0 = chain_init<W, NW>(sm, P, q0, ct, bar, chain);
   FastRegs F;
-  if constexpr (FAST) fast_setup<W>(sm, ct, yv0, F);
+  if constexpr (FAST != 0) fast_setup<W>(sm, ct, yv0, F);
+  if constexpr (FAST == 2) fast2_setup<W>(sm, P, ct);
   const int* wposv = reinterpret_cast<const int*>(sm + L.wpos);
   const int* wposTv = reinterpret_cast<const int*>(sm + L.wposT);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
@@ -935,7 +1169,8 @@ __global__ void __launch_bounds__(128, VIHMC_SMALL_MINBLOCKS) mlp_small_sample_k
         sm[L.p + i] = pv;
       };
       float ll_lane;
-      if constexpr (FAST) ll_lane = eval_fast<W>(sm, P, lik, ct, F, consume);
+      if constexpr (FAST == 2) ll_lane = eval_fast2<W>(sm, P, lik, ct, F, consume);
+      else if constexpr (FAST == 1) ll_lane = eval_fast<W>(sm, P, lik, ct, F, consume);
       else ll_lane = eval_likelihood_grad<W, NW>(sm, P, lik, ct, bar, yv0, consume);
       if (first || last) {
         const float lp = chain_sum<NW>(fmaf(lp_lane, P.inv_prior_scale, ll_lane), red, ct, bar) + log_norm;
@@ -1008,7 +1243,7 @@ enum SmallOp { kOpLogpGrad = 0, kOpPredict = 1, kOpSample = 2, kOpSensitivity = 
 
 struct SmallLaunch {
   int warps_per_chain, chains_per_block, blocks;
-  int fast;   // specialised 1-W-W-1 tanh single-chunk evaluation (eval_fast)
+  int fast;   // specialised 1-W-W-1 tanh single-chunk evaluation: 1 = eval_fast, 2 = eval_fast2 (register partial sums, W <= 16)
   size_t smem;
   long long C;
   const float* q;
@@ -1024,7 +1259,7 @@ static int set_smem(K kernel, size_t bytes) {
   return VIHMC_OK;
 }
 
-template <int W, int NW, bool FAST>
+template <int W, int NW, int FAST>
 static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
   const int threads = a.chains_per_block * 32 * NW;
   if (op == kOpLogpGrad) {
@@ -1053,9 +1288,12 @@ static int launch_small_wn(SmallOp op, const SmallParams& P, const SmallLaunch& 
 
 template <int W>
 static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
-  if (a.warps_per_chain == 2) return launch_small_wn<W, 2, false>(op, P, a, st);
-  if (a.fast) return launch_small_wn<W, 1, true>(op, P, a, st);
-  return launch_small_wn<W, 1, false>(op, P, a, st);
+  if (a.warps_per_chain == 2) return launch_small_wn<W, 2, 0>(op, P, a, st);
+  if constexpr (W <= 16) {   // version 2 keeps 2 W quads in registers: widths above 16 stay on version 1
+    if (a.fast == 2) return launch_small_wn<W, 1, 2>(op, P, a, st);
+  }
+  if (a.fast) return launch_small_wn<W, 1, 1>(op, P, a, st);
+  return launch_small_wn<W, 1, 0>(op, P, a, st);
 }
 
 }  // namespace vihmc
