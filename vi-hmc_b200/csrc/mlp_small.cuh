@@ -30,6 +30,7 @@ constexpr int kMaxHidden = 4;
 #ifndef VIHMC_SMALL_MINBLOCKS
 #define VIHMC_SMALL_MINBLOCKS 4   // register budget of the small-MLP kernels: 65536 / (128 * minblocks) = 128
 #endif
+constexpr int kRegRounds = 2;   // FAST == 3: sampled coordinates per lane held in registers (d <= 64)
 #ifndef VIHMC_SMALL_MINBLOCKS2
 #define VIHMC_SMALL_MINBLOCKS2 2  // eval_fast2 keeps 2 W activation quads in registers: 255 registers per thread
 #endif
@@ -790,9 +791,9 @@ __device__ __forceinline__ float quad_dot(unsigned long long a01, unsigned long 
   return lo + hi;
 }
 
-template <int W, typename Consume>
-__device__ __forceinline__ float eval_fast2(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F,
-                                            Consume&& consume) {
+// forward, backward and the partial sums; on return (after a warp barrier) part[] holds the partial gradient sums of every lane
+template <int W>
+__device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F) {
   constexpr SmallLayout L0c = make_layout(W, 2, 1, 0, true);   // weight / activation offsets do not depend on d
   constexpr int NC = L0c.NC, NCS = L0c.NCS, WSW = round_up(W, 4), JP = W / 2, NQ = NC / 4;
   const SmallLayout& L = P.lay;
@@ -906,17 +907,29 @@ __device__ __forceinline__ float eval_fast2(float* sm, const SmallParams& P, con
     pt[(2 * W + 8) * 33] = (dO[0] + dO[1]) + (dO[2] + dO[3]);
   }
   __syncwarp();
-  {  // owner lane of a sampled coordinate: the NQ partials of its coordinate, fixed order
-    const int* pm = reinterpret_cast<const int*>(sm + L.pmeta);
-    const float* part = sm + L.part;
-    for (int i = ct; i < (int)P.d; i += 32) {
-      const float* pp = part + pm[i];
-      float gsum = pp[0];
+  return ll_lane;
+}
+
+// likelihood gradient of the coordinate whose partial sums start at part[poff]: the NQ partials in fixed order
+template <int W>
+__device__ __forceinline__ float fast2_reduce(const float* sm, const SmallParams& P, int poff) {
+  constexpr int JP = W / 2, NQ = ((32 / W) * 8) / 4;
+  const float* pp = sm + P.lay.part + poff;
+  float v[NQ];
 #pragma unroll
-      for (int nq = 1; nq < NQ; ++nq) gsum += pp[nq * JP];
-      consume(i, gsum);
-    }
-  }
+  for (int nq = 0; nq < NQ; ++nq) v[nq] = pp[nq * JP];
+  float gsum = v[0];
+#pragma unroll
+  for (int nq = 1; nq < NQ; ++nq) gsum += v[nq];
+  return gsum;
+}
+
+template <int W, typename Consume>
+__device__ __forceinline__ float eval_fast2(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F,
+                                            Consume&& consume) {
+  const float ll_lane = eval_fast2_partials<W>(sm, P, lik, ct, F);
+  const int* pm = reinterpret_cast<const int*>(sm + P.lay.pmeta);
+  for (int i = ct; i < (int)P.d; i += 32) consume(i, fast2_reduce<W>(sm, P, pm[i]));
   __syncwarp();
   return ll_lane;
 }
@@ -925,7 +938,7 @@ __device__ __forceinline__ float eval_fast2(float* sm, const SmallParams& P, con
 // kernel 1: log-posterior value + gradient for C chains (vihmc_logp_grad, MLP small path)
 // ------------------------------------------------------------------------------------------------
 template <int W, int NW, int FAST>
-__global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C,
+__global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHMC_SMALL_MINBLOCKS) mlp_small_logp_grad_kernel(SmallParams P, long long C,
                                                                                          const float* __restrict__ q,
                                                                                          float* __restrict__ logp,
                                                                                          float* __restrict__ grad) {
@@ -945,7 +958,7 @@ __global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
     if (grad != nullptr) grad[chain * P.d + i] = fmaf(-dq * iv, P.inv_prior_scale, gl);
   };
   float ll_lane;
-  if constexpr (FAST == 2) {
+  if constexpr (FAST >= 2) {
     FastRegs F;
     fast_setup<W>(sm, ct, yv0, F);
     fast2_setup<W>(sm, P, ct);
@@ -1048,7 +1061,7 @@ struct SampleArgs {
 };
 
 template <int W, int NW, int FAST>
-__global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
+__global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHMC_SMALL_MINBLOCKS) mlp_small_sample_kernel(SmallParams P, SampleArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr int T = Cfg<W, NW>::T;
   const int ct = threadIdx.x % T, slot = threadIdx.x / T, bar = 1 + slot;
@@ -1063,7 +1076,30 @@ __global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
   const float yv0 = chain_init<W, NW>(sm, P, q0, ct, bar, chain);
   FastRegs F;
   if constexpr (FAST != 0) fast_setup<W>(sm, ct, yv0, F);
-  if constexpr (FAST == 2) fast2_setup<W>(sm, P, ct);
+  if constexpr (FAST >= 2) fast2_setup<W>(sm, P, ct);
+  // FAST == 3 (d <= 32 kRegRounds): the lane owns coordinates ct, ct + 32, ...; their constants live in registers for the whole run
+  // and q, p for the length of a trajectory (ncu of FAST == 2: the dependent shared-memory round trips of the coordinate loop --
+  // q, prior, p, table positions, then the stores -- were 29 % of all stall samples)
+  constexpr int NR = FAST == 3 ? kRegRounds : 1;
+  int r_pm[NR], r_wpos[NR], r_wposT[NR];
+  float r_pmu[NR], r_piv[NR], r_q[NR], r_p[NR];
+  bool r_ok[NR];
+  if constexpr (FAST == 3) {
+    const int* pmv = reinterpret_cast<const int*>(sm + L.pmeta);
+    const int* wpv = reinterpret_cast<const int*>(sm + L.wpos);
+    const int* wtv = reinterpret_cast<const int*>(sm + L.wposT);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int i = ct + 32 * r;
+      r_ok[r] = i < (int)P.d;
+      r_pm[r] = r_ok[r] ? pmv[i] : 0;
+      r_wpos[r] = r_ok[r] ? wpv[i] : 0;
+      r_wposT[r] = r_ok[r] ? wtv[i] : -1;
+      r_pmu[r] = r_ok[r] ? sm[L.pmu + i] : 0.0f;
+      r_piv[r] = r_ok[r] ? sm[L.piv + i] : 0.0f;
+      r_q[r] = r_p[r] = 0.0f;
+    }
+  }
   const int* wposv = reinterpret_cast<const int*>(sm + L.wpos);
   const int* wposTv = reinterpret_cast<const int*>(sm + L.wposT);
   const Likelihood lik = make_likelihood(P.loss, P.tau_out);
@@ -1145,10 +1181,47 @@ __global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
     // ---- trajectory: evaluation s = 0 yields H0 and the first half kick; s = nsteps yields H1 ----
     const float half_eps = 0.5f * eps;
     float logp0 = 0.0f, logp1 = 0.0f, ke1 = 0.0f;
+    if constexpr (FAST == 3) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (r_ok[r]) { r_q[r] = sm[L.q + ct + 32 * r]; r_p[r] = sm[L.p + ct + 32 * r]; }
+    }
     for (int s = 0; s <= nsteps; ++s) {
       const bool first = s == 0, last = s == nsteps;
       const float kick = first ? half_eps : eps;
       float lp_lane = 0.0f, ke_lane = 0.0f;
+      if constexpr (FAST == 3) {   // the operations of consume() below on the register copies, all rounds in flight together
+        const float ll3 = eval_fast2_partials<W>(sm, P, lik, ct, F);
+        float gl[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) gl[r] = fast2_reduce<W>(sm, P, r_pm[r]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (r_ok[r]) {
+            const float dq = r_q[r] - r_pmu[r], iv = r_piv[r];
+            lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
+            const float gi = fmaf(-dq * iv, P.inv_prior_scale, gl[r]);
+            float pv = axpy_unfused(kick, gi, r_p[r]);
+            if (last) {
+              pv = __fsub_rn(pv, __fmul_rn(half_eps, gi));
+              ke_lane = fmaf(pv, pv, ke_lane);
+            } else {
+              const float qv = axpy_unfused(eps, pv, r_q[r]);
+              r_q[r] = qv;
+              sm[r_wpos[r]] = qv;
+              if (r_wposT[r] >= 0) sm[r_wposT[r]] = qv;
+            }
+            r_p[r] = pv;
+          }
+        }
+        __syncwarp();
+        if (first || last) {
+          const float lp = chain_sum<NW>(fmaf(lp_lane, P.inv_prior_scale, ll3), red, ct, bar) + log_norm;
+          if (first) logp0 = lp;
+          if (last) { logp1 = lp; ke1 = 0.5f * chain_sum<NW>(ke_lane, red, ct, bar); }
+        }
+        continue;
+      }
       auto consume = [&](int i, float gl) {
         const float qv0 = sm[L.q + i];
         const float dq = qv0 - sm[L.pmu + i], iv = sm[L.piv + i];
@@ -1178,6 +1251,12 @@ __global__ void __launch_bounds__(128, FAST == 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
         if (last) { logp1 = lp; ke1 = 0.5f * chain_sum<NW>(ke_lane, red, ct, bar); }
       }
       chain_sync<NW>(bar);
+    }
+    if constexpr (FAST == 3) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (r_ok[r]) sm[L.q + ct + 32 * r] = r_q[r];
+      __syncwarp();
     }
     const float H0 = -logp0 + ke0, H1 = -logp1 + ke1;
     if (n == 0) {
@@ -1290,6 +1369,7 @@ template <int W>
 static int launch_small_w(SmallOp op, const SmallParams& P, const SmallLaunch& a, cudaStream_t st) {
   if (a.warps_per_chain == 2) return launch_small_wn<W, 2, 0>(op, P, a, st);
   if constexpr (W <= 16) {   // version 2 keeps 2 W quads in registers: widths above 16 stay on version 1
+    if (a.fast == 2 && op == kOpSample && P.d <= 32 * kRegRounds) return launch_small_wn<W, 1, 3>(op, P, a, st);
     if (a.fast == 2) return launch_small_wn<W, 1, 2>(op, P, a, st);
   }
   if (a.fast) return launch_small_wn<W, 1, 1>(op, P, a, st);
