@@ -65,7 +65,7 @@ static int fill_params(const vihmc_problem* p, SmallParams& P, int& W, long long
   fast = allow_fast && fast_path_enabled() && warps_per_chain_for(C) == 1 && nh == 2 && p->in_a == 1 && p->act == VIHMC_ACT_TANH &&
          p->N <= (32 / W) * 8;
   if (fast && W <= 16 && p->last_bias) fast = fast_version();
-  P.lay = make_layout(W, nh, p->in_a, p->d, fast != 0);
+  P.lay = make_layout(W, nh, p->in_a, p->d, fast);
   return VIHMC_OK;
 }
 

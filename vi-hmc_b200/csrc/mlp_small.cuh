@@ -49,6 +49,8 @@ struct SmallLayout {
   // per-coordinate state, each dp entries
   int coord_base, dp, q, p, g, qf, pmu, piv, meta, wpos, wposT, red;
   int part, pmeta;   // specialised path v2: per-lane partial gradient sums [2W+9 slots][33] and each coordinate's offset into them
+  int perm;          // v2, register-resident coordinates: coordinate index of (lane, round), 64 entries (-1: none)
+  int rot;           // v2: hidden->hidden tables in schedule order (column 2m + h of row j holds unit fast2_unit_at(JP, j % JP, m) + JP h)
   int total;
 };
 
@@ -70,8 +72,22 @@ __host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / 
 // lane = (unit pair jp, point quad nq) mapping, so the float4 row stores are conflict-free (found by enumeration).
 __host__ __device__ constexpr int fast_ncs(int W) { return W == 10 ? 52 : W == 16 ? 20 : W == 32 ? 12 : ((32 / W) * 8 + 4); }
 
+// Version 2 of the specialised path (eval_fast2): activation rows 64 floats apart, row r shifted by fast2_rowshift floats.
+// Its contractions skip the lane's own two rows and read the others on a "spare row" schedule -- step m reads row m - 1,
+// except the lane that owns row m - 1, which reads row JP - 1 -- so a quarter warp touches two rows per load.  The shifts
+// (16-byte chunks mod 8) make those LDS.128 conflict-free for lane = jp + JP nq; found by enumeration for JP = 5 (the row
+// stores then cost 6 wavefronts per 4 quarter warps instead of 4), trivial for JP = 8 (a quarter warp is one point quad).
+__host__ __device__ constexpr int fast2_rowshift(int W, int r) {
+  const int jp = r % (W / 2);
+  return W == 10 ? 4 * (jp == 0 ? 0 : jp == 1 ? 2 : jp == 2 ? 3 : jp == 3 ? 7 : 5) : 4 * (jp % 8);
+}
+__host__ __device__ constexpr int fast2_rowoff(int W, int r) { return r * 64 + fast2_rowshift(W, r); }
+// unit read at step m (m = 0: the lane's own) by the lane owning units jp, jp + JP; and the inverse (column of unit kk)
+__host__ __device__ constexpr int fast2_unit_at(int JP, int jp, int m) { return m == 0 ? jp : (m - 1 != jp ? m - 1 : JP - 1); }
+__host__ __device__ constexpr int fast2_step_of(int JP, int jp, int kk) { return kk == jp ? 0 : (kk == JP - 1 ? jp + 1 : kk + 1); }
+
 // W = padded hidden width the kernel is compiled for; fast = layout of the specialised 1-W-W-1 tanh path
-__host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, bool fast = false) {
+__host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, int fast = 0) {
   SmallLayout L{};
   const int WSW = round_up(W, 4);
   int off = 0;
@@ -87,7 +103,7 @@ __host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int i
   }
   L.w_total = off;
   L.NC = (32 / W) * 8;
-  L.NCS = fast ? fast_ncs(W) : L.NC + 4;   // +4: eight different rows land in eight different bank groups
+  L.NCS = fast >= 2 ? 64 : fast ? fast_ncs(W) : L.NC + 4;   // +4: eight different rows land in eight different bank groups
   L.act_base = off;
   int a = 0;
   L.xs = a; a += in_dim * L.NCS;
@@ -112,6 +128,8 @@ __host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int i
   L.red = off; off += 8;      // cross-warp reduction slots (two warps per chain)
   L.pmeta = off; off += fast ? L.dp : 0;
   L.part = off; off += fast ? (2 * W + 9) * 33 + 3 : 0;
+  L.perm = off; off += fast ? 64 : 0;
+  L.rot = fast >= 2 ? 1 : 0;
   L.total = off;
   return L;
 }
@@ -132,6 +150,11 @@ __device__ __forceinline__ void decode_coord(const SmallParams& P, int W, long l
       const int j = (int)((f - base) / in_l), k = (int)((f - base) % in_l);
       wpos = L.wbase[l] + j * L.ws[l] + k;
       if (l >= 1 && l < P.n_hidden) wposT = L.tbase[l] + k * WSW + j;
+      if (L.rot && l >= 1 && l < P.n_hidden) {
+        const int JP = W / 2;
+        wpos = L.wbase[l] + j * L.ws[l] + 2 * fast2_step_of(JP, j % JP, k % JP) + k / JP;
+        wposT = L.tbase[l] + k * WSW + 2 * fast2_step_of(JP, k % JP, j % JP) + j / JP;
+      }
       a_off = arow + (l < P.n_hidden ? j * L.NCS : 0);
       b_off = l == 0 ? L.xs + k * L.NCS : L.h + ((l - 1) * W + k) * L.NCS;
       return;
@@ -535,6 +558,8 @@ struct FastRegs {
   float x[4];   // the lane's 4 inputs (unit mode)
   float yv;     // the lane's target (point mode)
   float y4[4];  // the targets of the lane's 4 points (version 2: every lane of a point quad forms the residual)
+  int roff[7];  // version 2: activation-row offsets (floats) of the units read at steps m = 1 .. JP - 1 (W <= 16: JP <= 8)
+  int own_off;  // version 2: offset of the lane's own first row
 };
 
 // Unit-mode lane geometry of the specialised path: lane = (unit pair jp, point quad nq), i.e. a 2 x 4 register tile.
@@ -546,7 +571,8 @@ struct FastLane {
   static_assert(W % 2 == 0 && JP * NQ <= 32, "unit-mode lanes exceed the warp");
   bool unit;
   int j0, n0;   // the lane's units are j0 and j0 + JP (weight rows 12 floats apart stay conflict-free over consecutive j0)
-  __device__ __forceinline__ explicit FastLane(int ct) : unit(ct < JP * NQ), j0(unit ? ct % JP : 0), n0(unit ? 4 * (ct / JP) : 0) {}
+  // spare lanes mimic the last unit lane: their (ignored) loads then hit the addresses of that lane and add no bank conflicts
+  __device__ __forceinline__ explicit FastLane(int ct) : unit(ct < JP * NQ), j0(unit ? ct % JP : JP - 1), n0(unit ? 4 * (ct / JP) : 4 * (NQ - 1)) {}
 };
 
 template <int W>
@@ -557,6 +583,9 @@ __device__ __forceinline__ void fast_setup(const float* sm, int ct, float yv0, F
   F.yv = yv0;
 #pragma unroll
   for (int t = 0; t < 4; ++t) F.y4[t] = __shfl_sync(0xffffffffu, yv0, (ln.n0 + t) & 31);   // lane n holds the target of point n
+#pragma unroll
+  for (int m = 1; m < 8; ++m) F.roff[m - 1] = m < W / 2 ? fast2_rowoff(W, fast2_unit_at(W / 2, ln.j0, m)) : 0;
+  F.own_off = fast2_rowoff(W, ln.j0);
 }
 
 // acc[u][t] += sum_k wrow_u[k] * rows[k][t], u < 2, t < 4, on packed pairs; k ascending as in dot_rows.
@@ -729,7 +758,8 @@ __device__ __forceinline__ int fast2_poff(const SmallParams& P, int W, long long
   else if (f < 2 * w0 + (long long)w1 * w0) {                                     // W1[j][k]
     const int r = (int)f - 2 * w0;
     j = r / w0;
-    return ((j / JP) * W + r % w0) * 33 + j % JP;
+    const int k = r % w0;
+    return ((j / JP) * W + 2 * fast2_step_of(JP, j % JP, k % JP) + k / JP) * 33 + j % JP;   // schedule order of the columns (dot_rows_rot)
   }
   else if (f < 2 * w0 + (long long)w1 * w0 + w1) { j = (int)f - 2 * w0 - w1 * w0; slot = 2 * W; }        // b1[j]
   else if (f < 2 * w0 + (long long)w1 * w0 + 2 * w1) { j = (int)f - 2 * w0 - w1 * w0 - w1; slot = 2 * W + 6; }   // W2[0][j]
@@ -743,20 +773,48 @@ __device__ __forceinline__ void fast2_setup(float* sm, const SmallParams& P, int
   int* pm = reinterpret_cast<int*>(sm + L.pmeta);
   for (int i = ct; i < (int)P.d; i += 32) pm[i] = fast2_poff(P, W, P.sens_ind ? __ldg(P.sens_ind + i) : (long long)i);
   __syncwarp();
+  // Register-resident coordinates (d <= 64): which coordinates share a ROUND decides the bank conflicts of the partial-sum
+  // loads (all lanes of a round read part[pm + nq JP] together; bank = pm mod 32).  Greedy split into two rounds: a coordinate
+  // goes to the round that holds fewer coordinates of its bank (then the emptier round).  ncu before: 3.5 wavefronts per load.
+  int* perm = reinterpret_cast<int*>(sm + L.perm);
+  for (int i = ct; i < 64; i += 32) perm[i] = -1;
+  __syncwarp();
+  if (ct == 0 && P.d <= 64) {
+    int* cnt = reinterpret_cast<int*>(sm + L.part);   // scratch: [2][32] coordinates of bank b in round r (part[] is free until the first evaluation)
+    for (int i = 0; i < 64; ++i) cnt[i] = 0;
+    int n0 = 0, n1 = 0;
+    for (int i = 0; i < (int)P.d; ++i) {
+      const int b = pm[i] & 31, c0 = cnt[b], c1 = cnt[32 + b];
+      const bool to1 = n0 >= 32 || (n1 < 32 && (c1 < c0 || (c1 == c0 && n1 < n0)));
+      if (to1) { perm[32 + n1++] = i; cnt[32 + b] = c1 + 1; }
+      else { perm[n0++] = i; cnt[b] = c0 + 1; }
+    }
+  }
+  __syncwarp();
 }
 
-// acc[u][t] += sum_k wrow_u[k] * rows[k][t] as dot_rows_2x4, and the loaded quads rows[k][n0 .. n0+3] are handed back in keep[k]
+// acc[u][t] += sum_k' wrow_u[k'] * quad(k')[t] with the schedule order of the v2 tables: column k' = 2m + h of the lane's
+// weight rows belongs to unit fast2_unit_at(JP, jp, m) + JP h.  m = 0 are the lane's own two units, whose quads it already holds
+// in registers (own[0], own[1]): only the 2 (JP - 1) quads of the other lanes of the point quad are read from shared memory.
+// keep[k'] hands all quads back (the operands of the weight-gradient partial sums).
 template <int W, int NCS>
-__device__ __forceinline__ void dot_rows_2x4_keep(const float* wrows, const float* rows, float (&acc)[2][4], ulonglong2 (&keep)[W]) {
-  constexpr int WSW = (W + 3) / 4 * 4;
+__device__ __forceinline__ void dot_rows_rot(const float* wrows, const float* rows, const int (&roff)[7], const ulonglong2 (&own)[2],
+                                             float (&acc)[2][4], ulonglong2 (&keep)[W]) {
+  constexpr int WSW = (W + 3) / 4 * 4, JP = W / 2;
   float w[2][WSW];
 #pragma unroll
   for (int u = 0; u < 2; ++u)
 #pragma unroll
     for (int k4 = 0; k4 < WSW / 4; ++k4) {
-      const float4 v = reinterpret_cast<const float4*>(wrows + u * (W / 2) * WSW)[k4];
+      const float4 v = reinterpret_cast<const float4*>(wrows + u * JP * WSW)[k4];
       w[u][4 * k4] = v.x; w[u][4 * k4 + 1] = v.y; w[u][4 * k4 + 2] = v.z; w[u][4 * k4 + 3] = v.w;
     }
+  keep[0] = own[0];
+  keep[1] = own[1];
+#pragma unroll
+  for (int m = 1; m < JP; ++m)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) keep[2 * m + h] = *reinterpret_cast<const ulonglong2*>(rows + roff[m - 1] + h * JP * 64);
   unsigned long long a[2][2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -765,13 +823,11 @@ __device__ __forceinline__ void dot_rows_2x4_keep(const float* wrows, const floa
   }
 #pragma unroll
   for (int k = 0; k < W; ++k) {
-    const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(rows + k * NCS);
-    keep[k] = r;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const unsigned long long ww = pack2(w[u][k], w[u][k]);
-      a[u][0] = ffma2(ww, r.x, a[u][0]);
-      a[u][1] = ffma2(ww, r.y, a[u][1]);
+      a[u][0] = ffma2(ww, keep[k].x, a[u][0]);
+      a[u][1] = ffma2(ww, keep[k].y, a[u][1]);
     }
   }
 #pragma unroll
@@ -779,6 +835,17 @@ __device__ __forceinline__ void dot_rows_2x4_keep(const float* wrows, const floa
     unpack2(a[u][0], acc[u][0], acc[u][1]);
     unpack2(a[u][1], acc[u][2], acc[u][3]);
   }
+}
+
+// p[i & 3] without branches (the compiler turns a chain of ?: on floats into divergent branches)
+__device__ __forceinline__ float select4(int i, const float (&p)[4]) {
+  float r;
+  asm("{\n\t.reg .pred q0, q1;\n\t.reg .f32 a, b;\n\t"
+      "setp.ne.s32 q0, %5, 0;\n\tsetp.ne.s32 q1, %6, 0;\n\t"
+      "selp.f32 a, %2, %1, q0;\n\tselp.f32 b, %4, %3, q0;\n\tselp.f32 %0, b, a, q1;\n\t}"
+      : "=f"(r)
+      : "f"(p[0]), "f"(p[1]), "f"(p[2]), "f"(p[3]), "r"(i & 1), "r"(i & 2));
+  return r;
 }
 
 // sum over the 4 points of a quad: a . b with a, b packed as (01, 23)
@@ -794,8 +861,8 @@ __device__ __forceinline__ float quad_dot(unsigned long long a01, unsigned long 
 // forward, backward and the partial sums; on return (after a warp barrier) part[] holds the partial gradient sums of every lane
 template <int W>
 __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParams& P, const Likelihood lik, int ct, const FastRegs& F) {
-  constexpr SmallLayout L0c = make_layout(W, 2, 1, 0, true);   // weight / activation offsets do not depend on d
-  constexpr int NC = L0c.NC, NCS = L0c.NCS, WSW = round_up(W, 4), JP = W / 2, NQ = NC / 4;
+  constexpr SmallLayout L0c = make_layout(W, 2, 1, 0, 2);   // weight / activation offsets do not depend on d
+  constexpr int NCS = L0c.NCS, WSW = round_up(W, 4), JP = W / 2;
   const SmallLayout& L = P.lay;
   float* act = sm + L0c.act_base;
   const FastLane<W> ln(ct);
@@ -808,7 +875,7 @@ __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParam
       const unsigned long long w2 = pack_f2(w, w), b2 = pack_f2(b, b);
       unpack_f2(tanh_sel2(fma_f2(w2, pack_f2(F.x[0], F.x[1]), b2)), h0[u][0], h0[u][1]);
       unpack_f2(tanh_sel2(fma_f2(w2, pack_f2(F.x[2], F.x[3]), b2)), h0[u][2], h0[u][3]);
-      if (ln.unit) store8(act + L0c.h + (j0 + u * JP) * NCS + n0, h0[u]);
+      if (ln.unit) store8(act + L0c.h + F.own_off + u * JP * 64 + n0, h0[u]);
     }
   }
   __syncwarp();
@@ -820,7 +887,9 @@ __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParam
 #pragma unroll
       for (int t = 0; t < 4; ++t) h1[u][t] = b;
     }
-    dot_rows_2x4_keep<W, NCS>(sm + L0c.wbase[1] + j0 * WSW, act + L0c.h + n0, h1, hk);
+    const ulonglong2 own[2] = {make_ulonglong2(pack_f2(h0[0][0], h0[0][1]), pack_f2(h0[0][2], h0[0][3])),
+                               make_ulonglong2(pack_f2(h0[1][0], h0[1][1]), pack_f2(h0[1][2], h0[1][3]))};
+    dot_rows_rot<W, NCS>(sm + L0c.wbase[1] + j0 * WSW, act + L0c.h + n0, F.roff, own, h1, hk);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       unpack_f2(tanh_sel2(pack_f2(h1[u][0], h1[u][1])), h1[u][0], h1[u][1]);
@@ -836,15 +905,24 @@ __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParam
     float part[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) part[t] = ln.unit ? fmaf(wo[1], h1[1][t], wo[0] * h1[0][t]) : 0.0f;
+    // a shuffle costs a wavefront of the shared-memory pipe like an LDS (tools/probe_shfl_lds.cu), so instead of all-gathering
+    // the JP x 4 partials (4 JP shuffles) the quad's lanes reduce-scatter them -- lane jp < 4 collects point jp: JP - 1 shuffles,
+    // the sender picks the partial its receiver wants -- and then gather the four totals (4 shuffles).  Fixed order per point.
     const int base = (ct / JP) * JP;
+    float tot = select4(j0, part);
+#pragma unroll
+    for (int r = 1; r < JP; ++r) {
+      int si = j0 - r;                       // the lane r places below (cyclically) collects point si
+      si += si < 0 ? JP : 0;
+      const float send = select4(si, part);
+      int src = j0 + r;
+      src -= src >= JP ? JP : 0;
+      tot += __shfl_sync(0xffffffffu, send, (base + src) & 31);
+    }
     float o[4];
     const float b2 = sm[L0c.bbase[2]];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] = b2;
-#pragma unroll
-    for (int m = 0; m < JP; ++m)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) o[t] += __shfl_sync(0xffffffffu, part[t], (base + m) & 31);
+    for (int t = 0; t < 4; ++t) o[t] = b2 + __shfl_sync(0xffffffffu, tot, (base + t) & 31);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const bool valid = ln.unit && n0 + t < (int)P.N;
@@ -866,7 +944,7 @@ __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParam
         asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(p), "l"(fma_f2(nh, h, one)));
         unpack_f2(q, dz1[u][t], dz1[u][t + 1]);
       }
-      if (ln.unit) store8(act + L0c.dz + (W + j0 + u * JP) * NCS + n0, dz1[u]);
+      if (ln.unit) store8(act + L0c.dz + W * NCS + F.own_off + u * JP * 64 + n0, dz1[u]);
     }
   }
   __syncwarp();
@@ -876,7 +954,9 @@ __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParam
 #pragma unroll
       for (int t = 0; t < 4; ++t) dz0[u][t] = 0.0f;
     ulonglong2 zk[W];   // not needed afterwards; the compiler drops it
-    dot_rows_2x4_keep<W, NCS>(sm + L0c.tbase[1] + j0 * WSW, act + L0c.dz + W * NCS + n0, dz0, zk);
+    const ulonglong2 own[2] = {make_ulonglong2(pack_f2(dz1[0][0], dz1[0][1]), pack_f2(dz1[0][2], dz1[0][3])),
+                               make_ulonglong2(pack_f2(dz1[1][0], dz1[1][1]), pack_f2(dz1[1][2], dz1[1][3]))};
+    dot_rows_rot<W, NCS>(sm + L0c.tbase[1] + j0 * WSW, act + L0c.dz + W * NCS + n0, F.roff, own, dz0, zk);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const unsigned long long one = pack_f2(1.0f, 1.0f);
@@ -911,13 +991,14 @@ __device__ __forceinline__ float eval_fast2_partials(float* sm, const SmallParam
 }
 
 // likelihood gradient of the coordinate whose partial sums start at part[poff]: the NQ partials in fixed order
+// (quads beyond the data, nq >= nq_used = ceil(N / 4), hold zeros and are not read)
 template <int W>
-__device__ __forceinline__ float fast2_reduce(const float* sm, const SmallParams& P, int poff) {
+__device__ __forceinline__ float fast2_reduce(const float* sm, const SmallParams& P, int poff, int nq_used) {
   constexpr int JP = W / 2, NQ = ((32 / W) * 8) / 4;
   const float* pp = sm + P.lay.part + poff;
   float v[NQ];
 #pragma unroll
-  for (int nq = 0; nq < NQ; ++nq) v[nq] = pp[nq * JP];
+  for (int nq = 0; nq < NQ; ++nq) v[nq] = nq < nq_used ? pp[nq * JP] : 0.0f;
   float gsum = v[0];
 #pragma unroll
   for (int nq = 1; nq < NQ; ++nq) gsum += v[nq];
@@ -929,7 +1010,8 @@ __device__ __forceinline__ float eval_fast2(float* sm, const SmallParams& P, con
                                             Consume&& consume) {
   const float ll_lane = eval_fast2_partials<W>(sm, P, lik, ct, F);
   const int* pm = reinterpret_cast<const int*>(sm + P.lay.pmeta);
-  for (int i = ct; i < (int)P.d; i += 32) consume(i, fast2_reduce<W>(sm, P, pm[i]));
+  const int nq_used = ((int)P.N + 3) / 4;
+  for (int i = ct; i < (int)P.d; i += 32) consume(i, fast2_reduce<W>(sm, P, pm[i], nq_used));
   __syncwarp();
   return ll_lane;
 }
@@ -1081,17 +1163,20 @@ __global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
   // and q, p for the length of a trajectory (ncu of FAST == 2: the dependent shared-memory round trips of the coordinate loop --
   // q, prior, p, table positions, then the stores -- were 29 % of all stall samples)
   constexpr int NR = FAST == 3 ? kRegRounds : 1;
-  int r_pm[NR], r_wpos[NR], r_wposT[NR];
+  int r_pm[NR], r_wpos[NR], r_wposT[NR], r_idx[NR];
+  const int nq_used = ((int)P.N + 3) / 4;
   float r_pmu[NR], r_piv[NR], r_q[NR], r_p[NR];
   bool r_ok[NR];
   if constexpr (FAST == 3) {
     const int* pmv = reinterpret_cast<const int*>(sm + L.pmeta);
     const int* wpv = reinterpret_cast<const int*>(sm + L.wpos);
     const int* wtv = reinterpret_cast<const int*>(sm + L.wposT);
+    const int* permv = reinterpret_cast<const int*>(sm + L.perm);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const int i = ct + 32 * r;
-      r_ok[r] = i < (int)P.d;
+      const int i = permv[ct + 32 * r];
+      r_idx[r] = i;
+      r_ok[r] = i >= 0;
       r_pm[r] = r_ok[r] ? pmv[i] : 0;
       r_wpos[r] = r_ok[r] ? wpv[i] : 0;
       r_wposT[r] = r_ok[r] ? wtv[i] : -1;
@@ -1184,7 +1269,7 @@ __global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
     if constexpr (FAST == 3) {
 #pragma unroll
       for (int r = 0; r < NR; ++r)
-        if (r_ok[r]) { r_q[r] = sm[L.q + ct + 32 * r]; r_p[r] = sm[L.p + ct + 32 * r]; }
+        if (r_ok[r]) { r_q[r] = sm[L.q + r_idx[r]]; r_p[r] = sm[L.p + r_idx[r]]; }
     }
     for (int s = 0; s <= nsteps; ++s) {
       const bool first = s == 0, last = s == nsteps;
@@ -1194,7 +1279,7 @@ __global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
         const float ll3 = eval_fast2_partials<W>(sm, P, lik, ct, F);
         float gl[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) gl[r] = fast2_reduce<W>(sm, P, r_pm[r]);
+        for (int r = 0; r < NR; ++r) gl[r] = fast2_reduce<W>(sm, P, r_pm[r], nq_used);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           if (r_ok[r]) {
@@ -1255,7 +1340,7 @@ __global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
     if constexpr (FAST == 3) {
 #pragma unroll
       for (int r = 0; r < NR; ++r)
-        if (r_ok[r]) sm[L.q + ct + 32 * r] = r_q[r];
+        if (r_ok[r]) sm[L.q + r_idx[r]] = r_q[r];
       __syncwarp();
     }
     const float H0 = -logp0 + ke0, H1 = -logp1 + ke1;
