@@ -815,25 +815,31 @@ __device__ __forceinline__ void dot_rows_rot(const float* wrows, const float* ro
   for (int m = 1; m < JP; ++m)
 #pragma unroll
     for (int h = 0; h < 2; ++h) keep[2 * m + h] = *reinterpret_cast<const ulonglong2*>(rows + roff[m - 1] + h * JP * 64);
-  unsigned long long a[2][2];
+  // eight independent chains (first / second half of the units x 2 units x 2 point pairs): with ~1.7 warps per scheduler the
+  // dependent-issue distance inside one warp decides the FFMA2 rate (ncu: "wait" was the largest stall reason)
+  unsigned long long a[2][2], b[2][2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     a[u][0] = pack2(acc[u][0], acc[u][1]);
     a[u][1] = pack2(acc[u][2], acc[u][3]);
+    b[u][0] = b[u][1] = 0ull;
   }
 #pragma unroll
-  for (int k = 0; k < W; ++k) {
+  for (int k = 0; k < W; k += 2) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const unsigned long long ww = pack2(w[u][k], w[u][k]);
-      a[u][0] = ffma2(ww, keep[k].x, a[u][0]);
-      a[u][1] = ffma2(ww, keep[k].y, a[u][1]);
+      const unsigned long long w0 = pack2(w[u][k], w[u][k]), w1 = pack2(w[u][k + 1], w[u][k + 1]);
+      a[u][0] = ffma2(w0, keep[k].x, a[u][0]);
+      a[u][1] = ffma2(w0, keep[k].y, a[u][1]);
+      b[u][0] = ffma2(w1, keep[k + 1].x, b[u][0]);
+      b[u][1] = ffma2(w1, keep[k + 1].y, b[u][1]);
     }
   }
+  const unsigned long long one = pack2(1.0f, 1.0f);
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    unpack2(a[u][0], acc[u][0], acc[u][1]);
-    unpack2(a[u][1], acc[u][2], acc[u][3]);
+    unpack2(ffma2(one, b[u][0], a[u][0]), acc[u][0], acc[u][1]);
+    unpack2(ffma2(one, b[u][1], a[u][1]), acc[u][2], acc[u][3]);
   }
 }
 
@@ -1280,24 +1286,20 @@ __global__ void __launch_bounds__(128, FAST >= 2 ? VIHMC_SMALL_MINBLOCKS2 : VIHM
         float gl[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) gl[r] = fast2_reduce<W>(sm, P, r_pm[r], nq_used);
+        // branch-free (selects and predicated stores; empty slots carry q = p = 0, zero prior weights and wposT = -1)
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          if (r_ok[r]) {
-            const float dq = r_q[r] - r_pmu[r], iv = r_piv[r];
-            lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
-            const float gi = fmaf(-dq * iv, P.inv_prior_scale, gl[r]);
-            float pv = axpy_unfused(kick, gi, r_p[r]);
-            if (last) {
-              pv = __fsub_rn(pv, __fmul_rn(half_eps, gi));
-              ke_lane = fmaf(pv, pv, ke_lane);
-            } else {
-              const float qv = axpy_unfused(eps, pv, r_q[r]);
-              r_q[r] = qv;
-              sm[r_wpos[r]] = qv;
-              if (r_wposT[r] >= 0) sm[r_wposT[r]] = qv;
-            }
-            r_p[r] = pv;
-          }
+          const float dq = r_q[r] - r_pmu[r], iv = r_piv[r];
+          lp_lane = fmaf(-0.5f * dq * dq, iv, lp_lane);
+          const float gi = r_ok[r] ? fmaf(-dq * iv, P.inv_prior_scale, gl[r]) : 0.0f;
+          const float pk = axpy_unfused(kick, gi, r_p[r]);
+          const float pv = last ? __fsub_rn(pk, __fmul_rn(half_eps, gi)) : pk;
+          ke_lane = fmaf(pv, pv, ke_lane);            // read only after the last evaluation
+          const float qv = axpy_unfused(eps, pv, r_q[r]);
+          r_q[r] = last ? r_q[r] : qv;
+          r_p[r] = pv;
+          if (!last && r_ok[r]) sm[r_wpos[r]] = qv;
+          if (!last && r_wposT[r] >= 0) sm[r_wposT[r]] = qv;
         }
         __syncwarp();
         if (first || last) {
