@@ -54,6 +54,7 @@ struct GemmArgs {
   // partial product to split_buf[(s*batch + b), M, N]; splits <= 1 means a plain GEMM
   int splits, kc, batch;
   int kc_hint;   // host side: preferred split-K slice length for this product (0: the default, splitk_chunk())
+  int slice_tiles;   // TMEM-A kernels: k-tiles per accumulation chain; the CTA sums its slices itself (0: one chain per CTA)
   float* split_buf;
   // row sums of opA over this CTA's K range (EPI_STORE, A staged MN-major, N <= 128): rowsum_part[(s*batch + b), M].
   // With opA = dZ^T these are the bias gradients sum_r dz[r, o], read off the operand stream the GEMM loads anyway.
@@ -356,7 +357,8 @@ __device__ __forceinline__ uint64_t step_desc(uint32_t tile_saddr, int mode, int
 enum { ACT_NONE = -1 };
 
 struct EpiCtx {
-  const float* tile;       // staged accumulators [BM][TILE_LD]
+  const float* tile;       // staged accumulators [BM][ld]
+  int ld;
   float* crow;             // C + (m0 + warp) * ldc + n0
   const float* arow;       // aux + (m0 + warp) * ld_aux + n0 (or null)
   const float* biasb;      // bias of this batch (EPI_BIAS_ACT)
@@ -383,7 +385,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiCtx& e, float& ll_acc, fl
     }
     return v;
   };
-  const float* trow = e.tile + e.warp * TILE_LD;
+  const float* trow = e.tile + e.warp * e.ld;
   float* crow = e.crow;
   const float* arow = e.arow;
   if (e.vec) {
@@ -416,7 +418,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiCtx& e, float& ll_acc, fl
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (r0 + RS * u < e.rows) {
-          const float4 v = *reinterpret_cast<const float4*>(trow + u * RS * TILE_LD + c);
+          const float4 v = *reinterpret_cast<const float4*>(trow + u * RS * e.ld + c);
           float4 o;
           o.x = apply(v.x, bv.x, av[u].x);
           o.y = nv > 1 ? apply(v.y, bv.y, av[u].y) : 0.0f;
@@ -425,7 +427,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiCtx& e, float& ll_acc, fl
           *reinterpret_cast<float4*>(crow + u * e.c_step + c) = o;
         }
       }
-      trow += U * RS * TILE_LD;
+      trow += U * RS * e.ld;
       crow += U * e.c_step;
       arow += U * e.a_step;
     }
@@ -442,7 +444,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiCtx& e, float& ll_acc, fl
         const float aux_v = (EPI == EPI_DACT || EPI == EPI_HEAD) ? __ldg(arow + c) : 0.0f;
         crow[c] = apply(trow[c], bias_v[j], aux_v);
       }
-      trow += (THREADS / 32) * TILE_LD;
+      trow += (THREADS / 32) * e.ld;
       crow += e.c_step;
       arow += e.a_step;
     }
@@ -456,15 +458,32 @@ __device__ __forceinline__ bool rows_vec_ok(const float* base, long long bs, lon
 // ATM (EPI_STORE, N <= 112, one n-tile): the A operand lives in tensor memory (see RowLoader); accumulators are 112 columns wide and
 // the single A stage takes the remaining 32 of the 256 allocated columns, so two CTAs per SM still hold TMEM at a time.
 constexpr int ATM_PF = 3;   // k-tiles of register prefetch in TMEM-A mode (see the main loop)
+// TMEM-A mode, round 2: the CTA sums its accumulation slices itself.  The tensor core's fp32 accumulate truncates, so a chain is
+// bounded to slice_tiles k-tiles (256 deep by default); in round 2's first version every slice was its own CTA and wrote a
+// partial tile (3 GB per DeepONet gradient batch, a fifth of the batch's time with the reduction kernel).  Now a CTA walks
+// several slices: at a slice boundary the 8 warps read the two accumulators (tcgen05.ld), add main + correction and then the
+// running sum -- a [128][116] fp32 tile in shared memory -- with round-to-nearest adds; the next slice starts a fresh chain.
+// Shared memory: the A stages are not used in this mode, so the B stages are packed (3 x 16 KB) and the sum tile follows:
+// 108.7 KB per CTA, still two CTAs per SM.  Cross-CTA splits remain only to fill the GPU.
+// Two B stages are enough here: every k-tile waits for the previous k-tile's MMAs anyway (one A stage in tensor memory), so
+// the stage of k-tile kt - 2 is free when k-tile kt is staged.  92 KB per CTA -- not more than before: with 2 x 109 KB the driver
+// picks the 233 KB shared-memory carve-out, and the ~20 KB of L1 that leaves made the K-major A stream (row-strided 32-byte
+// pieces, two k-tiles per 128-byte line) of the dxb product 1.7x slower.
+constexpr int ATM_STAGES = 2;
+constexpr int ATM_SUM_LD = ATM_ACCN + 4;
+constexpr int ATM_SUM_OFF = ATM_STAGES * 2 * TILE_BYTES;
+constexpr int SMEM_BYTES_ATM = ATM_SUM_OFF + BM * ATM_SUM_LD * 4 + 128;
 template <int EPI, bool ATM = false, int AM = -1, int BMD = -1>
 __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmArgs g, int a_mode, int b_mode) {
   constexpr bool RING = AM >= 0;   // compile-time staging modes + ATM_PF k-tiles of register prefetch (two CTAs per SM)
   if (AM >= 0) { a_mode = AM; b_mode = BMD; }   // compile-time staging modes (all TMEM-A kernels, and the K-major / K-major fast variant)
   constexpr int ACCN = ATM ? ATM_ACCN : BN;
+  constexpr int NST = ATM ? ATM_STAGES : STAGES;   // shared-memory stages
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // swizzled MN-major tiles need 1 KB-aligned bases
   unsigned char* smem = smem_raw;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SMEM_BYTES - 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BYTES - 64);
+  constexpr int SB = ATM ? SMEM_BYTES_ATM : SMEM_BYTES;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + SB - 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SB - 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool split = (EPI == EPI_STORE) && g.splits > 1;
   const int b = split ? (int)blockIdx.z / g.splits : (int)blockIdx.z;
@@ -481,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
   }
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&mbar[s], 1);
+    for (int s = 0; s < NST; ++s) mbar_init(&mbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -506,6 +525,36 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
   // One k-tile of register prefetch.  (Two tiles ahead was measured slower: 120+ registers leave room for only two
   // resident CTAs, and a third CTA parked in tcgen05.alloc is what hides the launch latency of the next tile.)
   const int nk = (g.K + BK - 1) / BK;
+  const int SL = (ATM && g.slice_tiles > 0) ? g.slice_tiles : nk;   // k-tiles per accumulation chain
+  float* sum_tile = reinterpret_cast<float*>(smem + ATM_SUM_OFF);
+  // slice boundary (TMEM-A mode): sum_tile (+)= main + correction accumulators; every MMA of the slice has completed
+  auto flush = [&](bool first_slice) {
+    const int q = warp & 3, half = warp >> 2;
+    float* srow = sum_tile + (q * 32 + lane) * ATM_SUM_LD + half * (ATM_ACCN / 2);
+#pragma unroll 1
+    for (int cc = 0; cc < ATM_ACCN / 2; cc += 8) {
+      if (half * (ATM_ACCN / 2) + cc >= g.N) break;
+      uint32_t r[8], rc[8];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (ATM_ACCN / 2) + cc);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(taddr));
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7])
+                   : "r"(taddr + (uint32_t)ATM_ACCN));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);   // main + corrections (RN)
+      if (!first_slice) {
+        const float4 s0 = *reinterpret_cast<const float4*>(srow + cc), s1 = *reinterpret_cast<const float4*>(srow + cc + 4);
+        v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+        v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+      }
+      *reinterpret_cast<float4*>(srow + cc) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(srow + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  };
   float4 ra[2], rb[2];
   const bool want_rowsum = (EPI == EPI_STORE) && g.rowsum_part != nullptr;   // host guarantees a_mode == LOAD_MNVEC
   float4 rs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -528,6 +577,7 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
     la.template fetch_t<AM>(0, ra);
     lb.template fetch_t<BMD>(0, rb);
   }
+  int sl_pos = 0;   // k-tile index inside the current accumulation slice (kept incrementally: no division in the loop)
   auto issue_mma = [&](int kt, unsigned char* st, int s) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t sa = smem_u32(st);
@@ -535,7 +585,7 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
     const int steps = k_left > 8 ? 2 : 1;
     for (int ks = 0; ks < steps; ++ks) {
       const uint64_t b_hi = step_desc(sa + 2 * TILE_BYTES, b_mode, ks), b_lo = step_desc(sa + 3 * TILE_BYTES, b_mode, ks);
-      const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
+      const uint32_t acc = ((ATM ? sl_pos : kt) > 0 || ks > 0) ? 1u : 0u;
       if (ATM) {
         const uint32_t ta = tmem_d + (uint32_t)ATM_ACOL + (uint32_t)ks * 8u;
         mma_tf32_ta(tmem_d, ta, b_hi, idesc, acc);
@@ -556,8 +606,10 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
       for (int i = 0; i < ATM_PF; ++i) {
         const int kt = kt0 + i;
         if (kt < nk) {
-          const int s = kt % STAGES;
-          unsigned char* st = smem + s * STAGE_BYTES;
+          const int s = kt % NST;
+          // (TMEM-A mode: packed B stages; the pointer is biased so that st + 2 TILE_BYTES is the stage's B_hi tile)
+          unsigned char* st = ATM ? smem + s * 2 * TILE_BYTES - 2 * TILE_BYTES : smem + s * STAGE_BYTES;
+          if (ATM) { sl_pos = (kt == 0 || sl_pos + 1 == SL) ? 0 : sl_pos + 1; }
           // one A stage in tensor memory: the MMAs of the previous k-tile must have read it (commits complete in order, so
           // this also frees the shared-memory stage of k-tile kt - STAGES)
           if (ATM) {
@@ -573,11 +625,12 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
               lr.template fetch<AM>(kt + ATM_PF, rva[i]);
               lb.template fetch_t<BMD>(kt + ATM_PF, rbb[i]);
             }
-            if (kt >= 1) mbar_wait(&mbar[(kt - 1) % STAGES], (uint32_t)((kt - 1) / STAGES) & 1u);
+            if (kt >= 1) mbar_wait(&mbar[(kt - 1) % NST], (uint32_t)((kt - 1) / NST) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (kt > 0 && sl_pos == 0) flush(kt == SL);   // slice boundary: bank the finished chain before the next one starts
             store_tmem(a_taddr, hi, lo);
           } else {
-            if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // shared-memory A: only the stage must be free
+            if (kt >= NST) mbar_wait(&mbar[s], (uint32_t)(kt / NST - 1) & 1u);   // shared-memory A: only the stage must be free
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (want_rowsum) {
 #pragma unroll
@@ -599,10 +652,10 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
     }
   }
   for (int kt = 0; !RING && kt < nk; ++kt) {
-    const int s = kt % STAGES;
+    const int s = kt % NST;
     unsigned char* st = smem + s * STAGE_BYTES;
     {
-      if (kt >= STAGES) mbar_wait(&mbar[s], (uint32_t)(kt / STAGES - 1) & 1u);   // the MMAs that read this stage are done
+      if (kt >= NST) mbar_wait(&mbar[s], (uint32_t)(kt / NST - 1) & 1u);   // the MMAs that read this stage are done
       if (want_rowsum) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) { rs[i].x += ra[i].x; rs[i].y += ra[i].y; rs[i].z += ra[i].z; rs[i].w += ra[i].w; }
@@ -636,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
       mma_commit(&mbar[s]);
     }
   }
-  mbar_wait(&mbar[(nk - 1) % STAGES], (uint32_t)((nk - 1) / STAGES) & 1u);   // commits complete in order: everything is done
+  mbar_wait(&mbar[(nk - 1) % NST], (uint32_t)((nk - 1) / NST) & 1u);   // commits complete in order: everything is done
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   if (ATM && want_rowsum && blockIdx.x == 0) {
@@ -678,8 +731,10 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
   // phase 1: TMEM -> registers -> shared tile [128][TILE_LD] (thread = one accumulator row, 8 columns per ld).
   // phase 2: coalesced pass: warp w owns rows w, w+8, ...; a warp instruction touches 512 contiguous bytes of
   // C / aux (each lane 4 columns), instead of 32 different rows as a row-per-thread epilogue would.
-  float* tile = reinterpret_cast<float*>(smem);   // operand stages are dead: every MMA has completed
-  {
+  float* tile = ATM ? sum_tile : reinterpret_cast<float*>(smem);   // operand stages are dead: every MMA has completed
+  if (ATM) {
+    flush(nk <= SL);   // the last slice; the sum tile is the staged tile of phase 2
+  } else {
     const int q = warp & 3, half = warp >> 2;
     float* trow = tile + (q * 32 + lane) * TILE_LD + half * (BN / 2);
 #pragma unroll 2
@@ -704,6 +759,7 @@ __global__ void __launch_bounds__(THREADS, AM >= 0 ? 2 : 3) tc_gemm_kernel(GemmA
   __syncthreads();
   EpiCtx e;
   e.tile = tile;
+  e.ld = ATM ? ATM_SUM_LD : TILE_LD;
   e.crow = g.C + (long long)b * g.c_bs + (long long)(m0 + warp) * g.ldc + n0;
   e.arow = (EPI == EPI_DACT || EPI == EPI_HEAD) ? g.aux + (long long)b * g.aux_bs + (long long)(m0 + warp) * g.ld_aux + n0 : nullptr;
   e.biasb = (EPI == EPI_BIAS_ACT) ? g.bias + (long long)b * g.bias_bs : nullptr;
@@ -892,7 +948,27 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
   g.splits = 1;
   g.batch = batch;
   const int chunk = g.kc_hint > 0 ? g.kc_hint : kSplitKChunk, thresh = chunk + chunk / 2;
-  if (EPI == EPI_STORE && scratch != nullptr && g.K > thresh) {
+  // VIHMC_TC_INSLICE=0: one accumulation chain per CTA as in the first round-2 version (A/B runs)
+  static const bool inslice = []() { const char* e = getenv("VIHMC_TC_INSLICE"); return e == nullptr || atoi(e) != 0; }();
+  g.slice_tiles = (use_atm && inslice) ? chunk / tc::BK : 0;
+  if (use_atm && inslice && scratch != nullptr && g.K > thresh) {
+    // TMEM-A kernels sum their slices in shared memory: cross-CTA splits only fill the GPU.  Cost of a choice in k-units per
+    // CTA slot: rounds x (slice-aligned K range + the partial tile's write and read, ~106 k-units of operand traffic)
+    const long long tiles = (long long)((g.M + tc::BM - 1) / tc::BM) * batch;
+    const int max_splits = (g.K + chunk - 1) / chunk;
+    const long long slots = 2LL * tc_num_sms();
+    long long best_cost = -1;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int kc = ((g.K + sp - 1) / sp + chunk - 1) / chunk * chunk;
+      if ((long long)kc * (sp - 1) >= g.K) continue;   // the last split would be empty
+      const long long rounds = (tiles * sp + slots - 1) / slots;
+      const long long cost = rounds * (kc + (sp > 1 ? 106 : 0));
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; g.kc = kc; }
+    }
+    g.splits = (g.K + g.kc - 1) / g.kc;
+    g.split_buf = scratch;
+    if ((long long)batch * g.splits > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch * splits > 65535");
+  } else if (EPI == EPI_STORE && scratch != nullptr && g.K > thresh) {
     // long reductions (dW = dZ^T X over thousands of rows): bound the length of one TMEM accumulation chain
     // (its fp32 accumulate truncates) and sum the slices with round-to-nearest adds
     // Slice length between 1024 (what the scratch is sized for) and 2048 (the accuracy bound), chosen so that the CTAs
@@ -940,10 +1016,10 @@ static int launch_tc_gemm(GemmArgs g, int batch, cudaStream_t st, float* scratch
     if (!configured_atm) {
       for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j)
-          VIHMC_CUDA_OK(cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+          VIHMC_CUDA_OK(cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES_ATM));
       configured_atm = true;
     }
-    table[a_mode][b_mode]<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(g, a_mode, b_mode);
+    table[a_mode][b_mode]<<<grid, tc::THREADS, tc::SMEM_BYTES_ATM, st>>>(g, a_mode, b_mode);
   } else if (a_mode == tc::LOAD_KVEC && b_mode == tc::LOAD_KVEC) {
     // both operands K-contiguous and aligned (the head product, the wide-MLP layers): staging modes fixed at compile time
     auto kk = tc::tc_gemm_kernel<EPI, false, tc::LOAD_KVEC, tc::LOAD_KVEC>;
