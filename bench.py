@@ -42,6 +42,7 @@ METRIC, UNIT = "chain-grad-evals/sec", "chain-grad-evals/s"
 _REAL_STDOUT_FD = None               # set when fd 1 is redirected (multi-GPU runs, see run_ours)
 CHAINS_PER_GPU = 1024
 D_SAMPLED, STEP_SIZE, L_STEPS, TAU_OUT = 40, 5e-4, 196, 0.0025
+WAVEFRONTS_PER_EVAL = 213.0   # shared-memory pipe cycles per chain-grad-eval of mlp_small_sample_kernel<10,1,3> (ncu, profiles/r02_summary.md F)
 FLOP_PER_GRAD_EVAL = 14_000          # 2*[3*N*sum(in*out) - N*in_1*out_1], N=20, 1-10-10-1
 REF_EVALS_PER_STEP = 16              # reference arm: bounded sample = 16 grad-evals per chain per step
 REPS = 7                             # timed launches of the headline leg; value = their median
@@ -284,14 +285,14 @@ def _subprocess_json(args, timeout):
 def cpu_baseline_leg():
     """Bounded CPU sample for our arm's JSON line: run the reference arm in a fresh process (no CUDA context)."""
     try:
-        return _subprocess_json(["--impl", "reference", "--steps", "60", "--warmup", "3"], 600)["cpu_baseline"]
+        return _subprocess_json(["--impl", "reference", "--steps", "700", "--warmup", "3"], 600)["cpu_baseline"]   # ~10 s of CPU work
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
 
 
 def don_cpu_baseline_leg():
     out = {}
-    for mode, evals in (("intra", 6), ("procs", 2)):
+    for mode, evals in (("intra", 150), ("procs", 16)):   # ~8 s each on 16 cores
         try:
             out[mode] = _subprocess_json(["--impl", "reference-cfg3", "--mode", mode, "--steps", str(evals)], 900)
         except Exception as e:  # pragma: no cover
@@ -606,17 +607,20 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False, legs="all"):
                      "note": "neither hbm nor tensor: 20x10x10 tiles are below any UMMA shape and all state lives in "
                              "shared memory; peak = 148 SM x 128 FMA lanes x 2 x sm_max_mhz (computed, not in "
                              "MEASURED_PEAKS.json); achieved = 14 kFLOP per chain-grad-eval (SURVEY 8(d)) / event time. "
-                             "ncu (profiles/r01_ncu_details_mlp_small_sample_final2.csv, profiles/r01_summary.md): the binding unit is "
-                             "the shared-memory pipe, l1tex lsu shared wavefronts 78 % of peak (303 per evaluation), 447 warp "
-                             "instructions per evaluation, issue slots 29 % busy; DRAM 217 KB read / 0 written per 40-iteration launch"},
-        # the unit that actually binds this kernel (ncu): shared-memory wavefronts.  303 wavefronts per chain-grad-eval is a constant
-        # of the compiled kernel (profiles/r01_ncu_details_mlp_small_sample_final2.csv: l1tex__data_pipe_lsu_wavefronts_mem_shared
-        # 2.446e9 for 1024 chains x 40 iterations x 197 evaluations); the pipe delivers one wavefront per clock per SM
-        "roofline_binding_unit": {"bound": "shared-memory pipe (l1tex lsu wavefronts)", "unit": "Gwavefronts/s",
-                                  "achieved": 303.0 * (CHAINS_PER_GPU * steps * (L_STEPS + 1)) / (ms * 1e-3) / 1e9,
+                             "ncu (profiles/r02_ncu_details_mlp_small_sample_v2.csv, profiles/r02_summary.md F): 213 shared-memory "
+                             "pipe cycles per evaluation (205 LDS/STS wavefronts + 8 shuffles), 520 warp instructions per "
+                             "evaluation, issue slots 43 % busy; the largest stall reason is the fixed-latency dependency wait "
+                             "inside a warp (1.7 warps per scheduler at 1024 chains); DRAM traffic negligible"},
+        # shared-memory pipe: LDS/STS wavefronts and shuffles share one wavefront per clock per SM (tools/probe_shfl_lds.cu).
+        # 213 pipe cycles per chain-grad-eval is a constant of the compiled kernel (ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared
+        # 8.30e7 for 1024 chains x 2 iterations x 197 evaluations = 205.6, plus the 8 SHFL of the output layer that metric omits)
+        "roofline_binding_unit": {"bound": "shared-memory pipe (l1tex lsu wavefronts + shuffles)", "unit": "Gwavefronts/s",
+                                  "achieved": WAVEFRONTS_PER_EVAL * (CHAINS_PER_GPU * steps * (L_STEPS + 1)) / (ms * 1e-3) / 1e9,
                                   "peak": 148 * sm_max_mhz * 1e6 / 1e9,
-                                  "frac": 303.0 * (CHAINS_PER_GPU * steps * (L_STEPS + 1)) / (ms * 1e-3) / (148 * sm_max_mhz * 1e6),
-                                  "wavefronts_per_chain_grad_eval": 303.0},
+                                  "frac": WAVEFRONTS_PER_EVAL * (CHAINS_PER_GPU * steps * (L_STEPS + 1)) / (ms * 1e-3) / (148 * sm_max_mhz * 1e6),
+                                  "wavefronts_per_chain_grad_eval": WAVEFRONTS_PER_EVAL,
+                                  "note": "round 1: 303 wavefronts at 0.78 of the pipe; version 2 of the kernel is bound by "
+                                          "dependent-issue latency, not by this pipe any more"},
         "cpu_baseline": cpu_baseline_leg() if (world == 1 and not skip_cpu) else None,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
                 "seconds": e2e_s, "timing": "median of 3 calls of samplers.sample with host tensors"},
