@@ -612,3 +612,42 @@ def test_long_run_posterior_predictive_matches_oracle_chains():
     acc_o = ref["accepted"].astype(np.float64)
     se_a = np.sqrt(acc_g.var(ddof=1) / Cg + acc_o.var(ddof=1) / chains_o)
     assert abs(acc_g.mean() - acc_o.mean()) < 4 * se_a + 1e-3, (acc_g.mean(), acc_o.mean(), se_a)
+
+
+@pytest.mark.parametrize("widths,n_pts,d", [((16, 16), 12, 40), ((12, 14), 16, 64), ((8, 8), 20, 30), ((10, 7), 20, 77),
+                                             ((16, 16), 16, 100), ((10, 10), 5, 141)])
+def test_specialised_v2_other_widths_and_point_counts(widths, n_pts, d):
+    """The version-2 evaluation is compiled for W = 10 and W = 16 (unit pairs JP = 5 / 8, different row shifts and shuffle groups)
+    and takes narrower / unequal layers as zero-padded ones; d <= 64 runs with the coordinate state in registers, d > 64 through
+    the callback path; fewer data points leave whole point quads empty.  Each variant: log-posterior and gradient against the fp64
+    oracle closure (norm-wise 2e-6 + the fp32 noise floor of the sum), and the persistent kernel against the general sampler
+    (built on the gradient kernel and the elementwise blocks) with the same momenta and uniforms."""
+    x, y, _, _ = cases.synth.bnn_data()
+    x, y = x[:n_pts].contiguous(), y[:n_pts].contiguous()
+    arch = cases.MLPArch(in_dim=1, widths=widths, out_dim=1, act="tanh", last_bias=True)
+    D = arch.num_params
+    d = min(d, D)
+    mu, sigma, _ = cases.synth.bnn_vi_artifacts(D, d, seed=3)
+    ind = np.sort(np.random.RandomState(11).choice(D, d, replace=False)).astype(np.int64)
+    sig = cases.sliced_prior_sigma(d, arch.tensor_numels(), [1.0] * 6)
+    spec = cases.LogProbSpec(arch=arch, x=x, y=y, loss="NLL", tau_out=0.0025, prior_sigma=torch.from_numpy(sig.astype(np.float32)),
+                             frozen=mu, sens_ind=ind, vi_sigma=sigma)
+    closure = oc.BnnLogProb(x=x, y=y, widths=widths, act="tanh", loss="NLL", tau_out=0.0025, prior=("sliced", [1.0] * 6),
+                            frozen=mu, sens_ind=ind, dtype=torch.float64)
+    rs = np.random.RandomState(5)
+    C = 9
+    q = torch.from_numpy((mu[ind].numpy()[None] + 0.05 * rs.randn(C, d)).astype(np.float32))
+    lp, gr = engine.logp_grad(spec, q)
+    for c in range(C):
+        lp_ref, g_ref = oc.value_and_grad(closure, q[c].double())
+        assert float(lp[c]) == pytest.approx(float(lp_ref), rel=2e-6)
+        err = float(torch.linalg.norm(gr[c].cpu().double() - g_ref)) / float(torch.linalg.norm(g_ref))
+        assert err < 5e-6, (widths, n_pts, d, c, err)
+    S, L, eps = 3, 11, 2e-4
+    p = torch.from_numpy(rs.randn(S, C, d).astype(np.float32))
+    u = torch.from_numpy(rs.uniform(0.05, 0.95, size=(S, C)).astype(np.float32))
+    a = engine.run_sampler([spec], q, S, L, eps, burn=0, inject_momenta=p, inject_uniforms=u)
+    b = engine.run_sampler([spec], q, S, L, eps, burn=0, inject_momenta=p, inject_uniforms=u, force_general=True)
+    np.testing.assert_allclose(a.hamiltonians.numpy(), b.hamiltonians.numpy(), rtol=2e-5, atol=2e-2)
+    assert torch.equal(a.accepted, b.accepted)
+    np.testing.assert_allclose(a.samples.numpy(), b.samples.numpy(), rtol=1e-4, atol=2e-6)
