@@ -573,6 +573,8 @@ def run_ours(steps, warmup, n_gpus, skip_cpu=False, legs="all"):
         if world == 1:
             tf32 = measure_tf32_peak(dev)
             configs["cfg3"] = don_leg(dev, tf32, skip_cpu)
+            from bench_multi import cfg5_leg
+            configs["cfg5"] = cfg5_leg(dev, rank, world, dist if world > 1 else None)   # the N = 1 point of the strong-scaling leg
         else:
             from bench_multi import cfg4_leg, cfg5_leg   # tools-free: lives next to this file
             configs["cfg4"] = cfg4_leg(dev, rank, world, dist)

@@ -19,9 +19,16 @@ CFG5_GFLOP = 472.4          # per chain-grad-eval over all 100k 
 def _max_over_ranks(dist, dev, value):
     import torch
 
+    if dist is None or not dist.is_initialized():
+        return float(value)
     t = torch.tensor([value], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _barrier(dist):
+    if dist is not None and dist.is_initialized():
+        dist.barrier()
 
 
 def cfg4_leg(dev, rank, world, dist):
@@ -89,7 +96,7 @@ def cfg5_leg(dev, rank, world, dist):
     kw = dict(num_samples=CFG5_SAMPLES, num_steps=CFG5_L, step_size=CFG5_EPS, burn=0, seed=5)
     vd.sample_data_sharded(local, q0, num_samples=1, num_steps=1, step_size=CFG5_EPS)      # warm-up
     torch.cuda.synchronize()
-    dist.barrier()
+    _barrier(dist)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = vd.sample_data_sharded(local, q0, **kw)
@@ -99,16 +106,18 @@ def cfg5_leg(dev, rank, world, dist):
     n_evals = CFG5_SAMPLES * (CFG5_L + 1)
     # the collectives alone: the same number of all-reduces of the same buffer, back to back
     buf = torch.zeros((CFG5_CHAINS, arch.num_params + 1), device=dev)
-    dist.all_reduce(buf)
-    torch.cuda.synchronize()
-    dist.barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record()
-    for _ in range(n_evals):
+    ar_ms = 0.0
+    if world > 1:
         dist.all_reduce(buf)
-    a1.record()
-    torch.cuda.synchronize()
-    ar_ms = _max_over_ranks(dist, dev, a0.elapsed_time(a1))
+        torch.cuda.synchronize()
+        _barrier(dist)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_evals):
+            dist.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = _max_over_ranks(dist, dev, a0.elapsed_time(a1))
     if rank != 0:
         return None
     evals = CFG5_CHAINS * n_evals

@@ -138,6 +138,29 @@ def test_wide_mlp_dense_path_vs_oracle():
     np.testing.assert_allclose(pred[0].numpy(), closure.forward(q[0].double()).detach().numpy()[:, 0], rtol=2e-5, atol=2e-5)
 
 
+def test_wide_mlp_many_rows_output_layer_gradient_on_the_transposed_product():
+    """cfg5's shape with enough rows (K = 3000 >= 512) that the single-row products take the tensor-core kernel: the output
+    layer's weight gradient dW[1, in] runs as the transposed problem (launch_gemm, M == 1), the first layer's dW[out, 1] as is,
+    and the long reductions go through the in-CTA slice sums.  Every tensor of the gradient against the fp64 oracle."""
+    arch = MLPArch(in_dim=1, widths=(64, 64), out_dim=1, act="tanh", last_bias=True)
+    x, y = synth.wide_bnn_data(n=3000, seed=3)
+    spec = LogProbSpec(arch=arch, x=x, y=y, loss="NLL", tau_out=0.0025, prior_sigma_scalar=1.0)
+    closure = oc.BnnLogProb(x=x, y=y, widths=(64, 64), loss="NLL", tau_out=0.0025,
+                            prior=("sliced", [1.0] * len(arch.tensor_numels())), dtype=torch.float64)
+    q = synth.default_linear_init(arch, seed=4).unsqueeze(0).repeat(2, 1)
+    q[1] += 0.05 * torch.from_numpy(np.random.RandomState(5).randn(arch.num_params).astype(np.float32))
+    logp, grad = engine.logp_grad(spec, q)
+    numels = arch.tensor_numels()
+    for c in range(2):
+        lp, gr = oc.value_and_grad(closure, q[c].double())
+        assert abs(float(logp[c]) - float(lp)) <= RTOL * abs(float(lp))
+        got, off = grad[c].cpu().double().numpy(), 0
+        for n_el in numels:      # per tensor, norm-wise: the output layer's weights are tensor 4 of 6
+            a_, b_ = got[off:off + n_el], gr.numpy()[off:off + n_el]
+            assert np.linalg.norm(a_ - b_) <= 1e-5 * np.linalg.norm(b_) + 1e-7, (c, off, n_el)
+            off += n_el
+
+
 # ---------------------------------------------------------------------------------------------
 # building blocks of the large-d path
 # ---------------------------------------------------------------------------------------------

@@ -170,6 +170,16 @@ static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scr
   if (batch > 65535) return fail(VIHMC_ERR_UNSUPPORTED, "gemm: batch > 65535");
   const bool tc = force < 0 ? tensor_cores_enabled() && tc_gemm_eligible(g) : force == 1;
   if (tc) return launch_tc_gemm<EPI>(g, batch, st, scratch, rowsum_part, rowsum_out, rowsum_bs, rowsum_done);
+  if (EPI == EPI_STORE && force < 0 && tensor_cores_enabled() && g.M == 1) {
+    // A single output row over a long reduction (the output layer's weight gradient dW[1, in] = dz^T[1, R] a[R, in] of the
+    // wide-BNN config: 22 ms per evaluation on the SIMT kernel, a third of the whole gradient): run the transposed problem
+    // C^T[in, 1] = a^T dz on the tensor-core kernel instead.  C^T's rows are one element long, so it is the same memory as C.
+    GemmArgs t = g;
+    t.A = g.B; t.a_bs = g.b_bs; t.a_sm = g.b_sn; t.a_sk = g.b_sk;
+    t.B = g.A; t.b_bs = g.a_bs; t.b_sk = g.a_sk; t.b_sn = g.a_sm;
+    t.M = g.N; t.N = 1; t.ldc = 1;
+    if (tc_gemm_eligible(t)) return launch_tc_gemm<EPI>(t, batch, st, scratch);   // no fused row sums: opA is not dz any more
+  }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
   sgemm_batched_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
   VIHMC_LAUNCH_OK("sgemm_batched_kernel");
