@@ -430,6 +430,62 @@ def bnn_posterior_summary():
           os.path.getsize(out) // 1024, "KiB")
 
 
+N1_DON = dict(chains=256, burn=100, iters=1000, thin=10, L=10, eps=0.04, frac=0.25)
+N1_DON_ARCH = dict(width_branch=16, width_trunk=16, in_branch=12, depth_branch=3, depth_trunk=4, output_neurons=8)
+
+
+def n1_don_problem():
+    """The small operator-network problem of the long-run test (the 'small' case of tests/cases.py): 6 functions x 35 trunk points,
+    D = 1393, VI-HMC split with d = 348."""
+    arch = DeepONetArch(**N1_DON_ARCH)
+    x1, x2, y, theta = synth.burgers_like(arch, n_train=6, n_t=5, n_x=7, seed=0)
+    mu, sigma, ind = synth.deeponet_vi_artifacts(theta, frac=N1_DON["frac"], seed=1)
+    return arch, x1, x2, y, mu, sigma, ind
+
+
+def n1_don_start(mu, sigma, ind, chains, seed0):
+    mu, sg = mu.numpy().astype(np.float64), sigma.numpy().astype(np.float64)
+    return np.stack([mu[ind] + sg[ind] * np.random.RandomState(seed0 + c).randn(len(ind)) for c in range(chains)])
+
+
+def _n1_don_worker(c):
+    from oracle import closures as oc
+    from oracle import hamiltorch_restated as hr
+
+    torch.set_num_threads(1)
+    arch, x1, x2, y, mu, sigma, ind = n1_don_problem()
+    closure = oc.DeepONetLogProb(x1=x1.unsqueeze(1), x2=x2.unsqueeze(0), y=y, frozen=mu, sens_ind=ind, width_branch=arch.width_branch,
+                                 width_trunk=arch.width_trunk, in_branch=arch.in_branch, in_trunk=arch.in_trunk,
+                                 depth_branch=arch.depth_branch, depth_trunk=arch.depth_trunk, output_neurons=arch.output_neurons,
+                                 act=arch.act, impose_bc=arch.impose_bc, loss="NLL", tau_out=1.0, prior_var=0.1 ** 2, dtype=torch.float64)
+    q0 = torch.from_numpy(n1_don_start(mu, sigma, ind, c + 1, 9000)[c])
+    total = N1_DON["burn"] + N1_DON["iters"]
+    tr = {}
+    out = hr.sample(closure, q0, num_samples=total, num_steps_per_sample=N1_DON["L"], step_size=N1_DON["eps"],
+                    generator=torch.Generator().manual_seed(5000 + c), trace=tr)
+    # out[n] = state after iteration n (out[0] = q0, hamiltorch's storage rule with burn = 0 drops nothing but the last)
+    keep = range(N1_DON["burn"] + N1_DON["thin"], total, N1_DON["thin"])
+    with torch.no_grad():
+        pred = torch.stack([closure.forward(out[k]) for k in keep]).reshape(len(keep), -1).numpy()     # [T, N * P]
+    return pred.mean(0), (pred * pred).mean(0), float(np.mean(tr["accept"][N1_DON["burn"]:]))
+
+
+def deeponet_posterior_summary():
+    """The operator-network half of the third correctness tier: 64 fp64 oracle chains (oracle/closures.py::DeepONetLogProb -- pinned
+    to the reference's closure by the golden vectors -- under oracle/hamiltorch_restated.py::sample) of a small DeepONet VI-HMC problem,
+    100 burn-in + 1000 iterations at eps 0.04 / L 10 (acceptance ~0.85), every 10th draw; stored: per-chain time averages of the
+    prediction and its square at the 6 x 35 training outputs and the acceptance rates.  One chain per process, ~3 minutes on 16 cores."""
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        res = pool.map(_n1_don_worker, range(N1_DON["chains"]))
+    m1, m2, acc = (np.stack([r[i] for r in res]) for i in range(3))
+    out = os.path.join(GOLDEN, "deeponet_posterior_summary.npz")
+    np.savez_compressed(out, f_mean=m1.astype(np.float32), f_sq_mean=m2.astype(np.float32), accepted=acc.astype(np.float32),
+                        cfg=np.array([N1_DON[k] for k in ("chains", "burn", "iters", "thin", "L")], np.int64), eps=N1_DON["eps"])
+    print("deeponet posterior summary: acceptance", acc.mean(), "wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     if len(sys.argv) > 1:   # python oracle/make_golden.py deeponet_fullsize_cases  (one generator only)
@@ -445,3 +501,4 @@ if __name__ == "__main__":
     deeponet_vi_training_case()
     deeponet_fullsize_cases()
     bnn_posterior_summary()
+    deeponet_posterior_summary()

@@ -161,6 +161,52 @@ def test_wide_mlp_many_rows_output_layer_gradient_on_the_transposed_product():
             off += n_el
 
 
+def test_long_run_posterior_predictive_small_deeponet_matches_oracle_chains():
+    """North-star tier 3 for the operator network (judge row N1, second half): 512 engine chains (general sampler on the dense
+    path: tcgen05 forward / backward, fused leapfrog and accept kernels) against the 256 fp64 oracle chains of
+    tests/golden/deeponet_posterior_summary.npz (oracle/make_golden.py::deeponet_posterior_summary): small DeepONet VI-HMC problem
+    (D = 1393, d = 348, 6 functions x 35 trunk points), same start law, eps 0.04, L 10 (acceptance ~0.77), 100 burn-in + 1000
+    iterations, every 10th draw.  As in the BNN test the unit of replication is the chain: per-chain time averages of f, f^2 and
+    the log within-chain variance at the 210 outputs, se^2 = var_engine / 512 + var_oracle / 256; max |z| < 4 per output, and mean z^2
+    per statistic below 6.6 (the outputs are so strongly correlated that a statistic has about one degree of freedom: the 1 % point
+    of chi^2_1), acceptance rates within 4 se."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import make_golden as mg
+
+    ref = cases.load_golden("deeponet_posterior_summary.npz")
+    chains_o, burn, iters, thin, L = (int(v) for v in ref["cfg"])
+    eps = float(ref["eps"])
+    arch, x1, x2, y, mu, sigma, ind = mg.n1_don_problem()
+    spec = LogProbSpec(arch=arch, x=x1, x2=x2, y=y, loss="NLL", tau_out=1.0, prior_sigma_scalar=0.1, frozen=mu, sens_ind=ind,
+                       vi_sigma=sigma)
+    Cg = 512
+    q0 = torch.from_numpy(mg.n1_don_start(mu, sigma, ind, Cg, 20000).astype(np.float32))
+    kw = dict(to_host=False, hamiltorch_fallback_rule=False)
+    warm = engine.run_sampler([spec], q0, burn, L, eps, burn=burn - 2, seed=5, **kw)
+    res = engine.run_sampler([spec], warm.samples[-1].contiguous(), iters + 1, L, eps, burn=0, seed=6, **kw)
+    draws = res.samples[thin::thin]
+    assert draws.shape[0] == iters // thin
+    pred = torch.stack([engine.predict(spec, d_).reshape(Cg, -1) for d_ in draws]).double()      # [T, C, N * P]
+    m1, m2 = pred.mean(0).cpu().numpy(), (pred * pred).mean(0).cpu().numpy()
+    o1, o2 = ref["f_mean"].astype(np.float64), ref["f_sq_mean"].astype(np.float64)
+    worst, zsq = [], []
+    for got, want in ((m1, o1), (m2, o2), (np.log(m2 - m1 * m1), np.log(o2 - o1 * o1))):
+        se = np.sqrt(got.var(0, ddof=1) / Cg + want.var(0, ddof=1) / chains_o)
+        z = (got.mean(0) - want.mean(0)) / se
+        worst.append(float(np.abs(z).max()))
+        zsq.append(float((z * z).mean()))
+    print(f"deeponet posterior predictive: max |z| {worst}, mean z^2 {zsq}")
+    assert max(worst) < 4.0 and max(zsq) < 6.6, (worst, zsq)
+    acc_g = res.accepted[1:].float().mean(0).cpu().numpy()
+    acc_o = ref["accepted"].astype(np.float64)
+    se_a = np.sqrt(acc_g.var(ddof=1) / Cg + acc_o.var(ddof=1) / chains_o)
+    print(f"acceptance engine {acc_g.mean():.4f} oracle {acc_o.mean():.4f} se {se_a:.4f}")
+    assert abs(acc_g.mean() - acc_o.mean()) < 4 * se_a + 1e-3, (acc_g.mean(), acc_o.mean(), se_a)
+
+
 # ---------------------------------------------------------------------------------------------
 # building blocks of the large-d path
 # ---------------------------------------------------------------------------------------------
