@@ -299,6 +299,11 @@ def test_data_sharded_sampler_equals_general_sampler():
     q0[1:] += 0.02 * torch.from_numpy(np.random.RandomState(3).randn(2, arch.num_params).astype(np.float32))
     kw = dict(num_samples=4, num_steps=5, step_size=2e-5, burn=1, seed=9)
     a = vd.sample_data_sharded(vd.shard_spec_rows(spec, 0, 1), q0, **kw)
+    assert a["graphs"]                          # the leapfrog steps replayed from CUDA graphs ...
+    e = vd.sample_data_sharded(vd.shard_spec_rows(spec, 0, 1), q0, use_graphs=False, **kw)
+    assert not e["graphs"]                      # ... are the eager loop bit for bit
+    for k in ("samples", "accepted", "hamiltonians"):
+        assert torch.equal(a[k], e[k]), k
     b = engine.run_sampler([spec], q0, force_general=True, **kw)
     assert torch.equal(a["accepted"].cpu(), b.accepted)
     np.testing.assert_allclose(a["samples"].cpu().numpy(), b.samples.numpy(), rtol=1e-5, atol=1e-6)

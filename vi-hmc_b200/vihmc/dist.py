@@ -116,14 +116,20 @@ def shard_spec_rows(spec, rank: Optional[int] = None, world_size: Optional[int] 
 
 
 def sample_data_sharded(spec_local, q0: torch.Tensor, num_samples: int, num_steps: int, step_size: float, burn: int = 0,
-                        seed: int = 0, hamiltorch_fallback_rule: bool = True) -> Dict[str, torch.Tensor]:
+                        seed: int = 0, hamiltorch_fallback_rule: bool = True, use_graphs: bool = True) -> Dict[str, torch.Tensor]:
     """HMC where every rank holds ALL chains and a row shard of the data (spec_local = shard_spec_rows(spec)).
 
     One exchange step per gradient evaluation: ONE all_reduce(SUM) of a [C, d + 1] buffer (gradients, log-posterior behind them);
     everything else is identical on every rank (same Philox streams), so all ranks make the same accept/reject
     decisions and hold the same samples.  The [C, d] arithmetic runs in the C-ABI building blocks
     (vihmc_logp_grad, vihmc_leapfrog_update, vihmc_momentum_philox, vihmc_mh_accept); torch does the collective
-    and the per-chain scalar adds.  Leapfrog order and rounding as in vihmc_sample / hamiltorch."""
+    and the per-chain scalar adds.  Leapfrog order and rounding as in vihmc_sample / hamiltorch.
+
+    ``use_graphs``: the three kinds of leapfrog step (first: H0 + half kick + drift; middle: kick + drift; last: kick, half kick
+    back, H1) -- gradient kernels, the packed all-reduce and the update kernels -- are each captured once into a CUDA graph (NCCL
+    collectives are capturable) and replayed: with 8 GPUs a step is well under a millisecond of ~40 short launches, and the
+    replay removes the launch gaps.  Same kernels, same order, same results as the eager loop
+    (tests/test_gpu_deeponet.py::test_data_sharded_sampler_equals_general_sampler compares the two bit for bit)."""
     from . import engine
 
     rank, w = world()
@@ -135,17 +141,27 @@ def sample_data_sharded(spec_local, q0: torch.Tensor, num_samples: int, num_step
     rows = num_samples - burn
     if rows < 1:
         raise RuntimeError("burn must be less than num_samples.")
+    if num_steps < 1:
+        raise ValueError("num_steps must be at least 1")
     samples = torch.empty((rows, C, d), dtype=torch.float32, device=dev)
     samples[0] = q0d
     accepted = torch.empty((num_samples, C), dtype=torch.uint8, device=dev)
     ham = torch.empty((num_samples, C, 2), dtype=torch.float32, device=dev)
     q_cur, q_fb = q0d.clone(), q0d.clone()
 
-    # ONE collective per evaluation: the [C] log-posteriors ride behind the [C, d] gradients in the same buffer
-    packed = torch.empty((C, d + 1), dtype=torch.float32, device=dev) if w > 1 else None
+    # Work buffers and graphs are cached on the prepared problem, keyed by what the captured launches depend on: a second call
+    # with the same chains / step size (the timed call after a warm-up, the next block of iterations) replays without re-capturing.
+    cache = prep.__dict__.setdefault("_data_sharded_cache", {})
+    key = (C, d, float(step_size), w, bool(use_graphs))
+    st = cache.get(key)
+    if st is None:
+        st = cache[key] = {"q": torch.empty_like(q0d), "p": torch.empty_like(q0d),
+                           # ONE collective per evaluation: the [C] log-posteriors ride behind the [C, d] gradients in the same buffer
+                           "packed": torch.empty((C, d + 1), dtype=torch.float32, device=dev) if w > 1 else None, "graphs": None}
+    q, p, packed = st["q"], st["p"], st["packed"]
 
-    def grad(q):
-        lp, g = engine.logp_grad(prep, q)
+    def grad(qq):
+        lp, g = engine.logp_grad(prep, qq)
         if w > 1:
             packed[:, :d].copy_(g)
             packed[:, d].copy_(lp)
@@ -154,22 +170,61 @@ def sample_data_sharded(spec_local, q0: torch.Tensor, num_samples: int, num_step
             lp.copy_(packed[:, d])
         return lp, g
 
-    for n in range(num_samples):
-        if hamiltorch_fallback_rule and n == burn + 1:
-            q_fb.copy_(q0d)
-        p = engine.momentum_philox(seed, n, 0, C, d, device=dev)
-        q = q_cur.clone()
+    def step_first():
         lp, g = grad(q)
         ke0 = engine.leapfrog_update(q, p, g, step_size, 0.0, 0.0, want_ke=True)     # kinetic energy of the fresh momentum
         h0 = ke0 - lp
         engine.leapfrog_update(q, p, g, step_size, 0.5, 1.0)
-        for s in range(1, num_steps + 1):
-            lp, g = grad(q)
-            engine.leapfrog_update(q, p, g, step_size, 1.0, 1.0 if s < num_steps else 0.0)
+        return h0
+
+    def step_mid():
+        lp, g = grad(q)
+        engine.leapfrog_update(q, p, g, step_size, 1.0, 1.0)
+
+    def step_last():
+        lp, g = grad(q)
+        engine.leapfrog_update(q, p, g, step_size, 1.0, 0.0)
         ke1 = engine.leapfrog_update(q, p, g, step_size, -0.5, 0.0, want_ke=True)
-        h1 = ke1 - lp
+        return ke1 - lp
+
+    # a trajectory of L steps: first, L - 1 middle evaluations, last (L + 1 gradient evaluations)
+    if use_graphs and dev.type == "cuda" and st["graphs"] is None:
+        q.copy_(q0d)
+        p.zero_()
+        step_mid()                                  # eager warm-up: lazy kernel attributes, workspace, NCCL channels
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        graphs = {}
+        with torch.cuda.device(dev):
+            for name, fn in (("first", step_first), ("mid", step_mid), ("last", step_last)):
+                q.copy_(q0d)
+                p.zero_()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    out = fn()
+                graphs[name] = (gr, out)
+        torch.cuda.synchronize(dev)
+        st["graphs"] = graphs
+    graphs = st["graphs"] if use_graphs else None
+
+    def run(name, fn):
+        if graphs is None:
+            return fn()
+        gr, out = graphs[name]
+        gr.replay()
+        return out
+
+    for n in range(num_samples):
+        if hamiltorch_fallback_rule and n == burn + 1:
+            q_fb.copy_(q0d)
+        p.copy_(engine.momentum_philox(seed, n, 0, C, d, device=dev))
+        q.copy_(q_cur)
+        h0 = run("first", step_first)
+        for s in range(1, num_steps):
+            run("mid", step_mid)
+        h1 = run("last", step_last)
         u = engine.uniform_philox(seed, n, 0, C, device=dev)
         store = n > burn
         engine.mh_accept(h0, h1, u, q, q_cur, q_fb, stored=samples[n - burn] if store else None, accepted=accepted[n])
         ham[n, :, 0], ham[n, :, 1] = h0, h1
-    return {"samples": samples, "accepted": accepted, "hamiltonians": ham}
+    return {"samples": samples, "accepted": accepted, "hamiltonians": ham, "graphs": graphs is not None}
