@@ -422,12 +422,15 @@ def don_leg(dev, peaks_tf32, skip_cpu):
     evals = DON_CHAINS * DON_SAMPLES * (DON_L + 1)
     engine.run_sampler([prep], q0, 1, 1, DON_EPS, to_host=False)             # warm-up: workspace, kernel attributes
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    res = engine.run_sampler([prep], q0, DON_SAMPLES, DON_L, DON_EPS, burn=0, seed=2, to_host=False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    runs_ms = []
+    for _ in range(3):            # median of three device-timed runs (single runs varied by up to 20 % between boxes / first use)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = engine.run_sampler([prep], q0, DON_SAMPLES, DON_L, DON_EPS, burn=0, seed=2, to_host=False)
+        e1.record()
+        torch.cuda.synchronize()
+        runs_ms.append(e0.elapsed_time(e1))
+    ms = sorted(runs_ms)[1]
     value = evals / (ms * 1e-3)
     acc = float(res.accepted.float().mean())
     dH = float((res.hamiltonians[..., 0] - res.hamiltonians[..., 1]).abs().median())
@@ -444,21 +447,28 @@ def don_leg(dev, peaks_tf32, skip_cpu):
     grad_ms = g0.elapsed_time(g1) / 2
     tflops = DON_GFLOP * DON_CHAINS / (grad_ms * 1e-3) / 1e3
     # end to end: host tensors in, host samples out
+    # (two full calls, the second is reported: the first one pays the one-off cudaHostAlloc of the 530 MB pinned result buffer and the
+    # cudaMalloc of the 37 GB workspace, which torch's caching allocators keep for every later call)
+    q0_pinned = q0_host.pin_memory()
     samplers.sample(spec, q0_host[:8], num_samples=1, num_steps_per_sample=1, step_size=DON_EPS)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = samplers.sample(spec, q0_host, num_samples=DON_SAMPLES, num_steps_per_sample=DON_L, step_size=DON_EPS, seed=3, return_result=True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_runs = []
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = samplers.sample(spec, q0_pinned, num_samples=DON_SAMPLES, num_steps_per_sample=DON_L, step_size=DON_EPS, seed=3, return_result=True)
+        torch.cuda.synchronize()
+        e2e_runs.append(time.perf_counter() - t0)
+    e2e_s = e2e_runs[-1]
     h2d = sum(t.numel() * t.element_size() for t in (spec.x, spec.x2, spec.y, q0_host))
     d2h = sum(x.numel() * x.element_size() for x in (out.samples, out.accepted, out.hamiltonians, out.logp, out.step_sizes))
     peak = peaks_tf32["tf32_tflops_sustained"]
     leg = {
         "workload": DON_WORKLOAD, "metric": METRIC, "unit": UNIT, "value": value, "ms_per_step": ms / DON_SAMPLES,
         "step": f"one HMC iteration of all {DON_CHAINS} chains = L+1 = {DON_L + 1} grad-evals per chain; {DON_SAMPLES} timed iterations",
-        "acceptance_rate": acc, "median_abs_energy_error": dH,
+        "acceptance_rate": acc, "median_abs_energy_error": dH, "run_ms": runs_ms,
         "e2e": {"value": evals / e2e_s, "unit": UNIT, "seconds": e2e_s, "h2d_bytes_per_step": h2d / DON_SAMPLES,
-                "d2h_bytes_per_step": d2h / DON_SAMPLES},
+                "d2h_bytes_per_step": d2h / DON_SAMPLES, "seconds_of_each_call": e2e_runs,
+                "timing": "second of two calls of samplers.sample with pinned host tensors (the first pays the one-off pinned / device allocations)"},
         "gradient_batch": {"chains": DON_CHAINS, "ms": grad_ms, "chain_grad_evals_per_s": DON_CHAINS / (grad_ms * 1e-3),
                            "tflops_fp32_equivalent": tflops},
         "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
