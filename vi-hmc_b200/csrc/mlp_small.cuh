@@ -86,6 +86,35 @@ __host__ __device__ constexpr int fast2_rowoff(int W, int r) { return r * 64 + f
 __host__ __device__ constexpr int fast2_unit_at(int JP, int jp, int m) { return m == 0 ? jp : (m - 1 != jp ? m - 1 : JP - 1); }
 __host__ __device__ constexpr int fast2_step_of(int JP, int jp, int kk) { return kk == jp ? 0 : (kk == JP - 1 ? jp + 1 : kk + 1); }
 
+// compile-time proofs of the two properties the version-2 contraction relies on
+constexpr bool fast2_schedule_is_a_permutation(int JP) {   // every lane visits every unit once, and step_of inverts unit_at
+  for (int jp = 0; jp < JP; ++jp) {
+    int seen = 0;
+    for (int m = 0; m < JP; ++m) {
+      const int u = fast2_unit_at(JP, jp, m);
+      if (u < 0 || u >= JP || (seen >> u & 1) || fast2_step_of(JP, jp, u) != m) return false;
+      seen |= 1 << u;
+    }
+  }
+  return true;
+}
+constexpr bool fast2_row_loads_conflict_free(int W) {   // per step and quarter warp: distinct 16-byte chunks hit distinct bank groups
+  const int JP = W / 2, NQ = ((32 / W) * 8) / 4;
+  for (int m = 1; m < JP; ++m)
+    for (int qw = 0; qw < 4; ++qw) {
+      int chunk_of_group[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+      for (int ct = 8 * qw; ct < 8 * qw + 8; ++ct) {
+        const int jp = ct < JP * NQ ? ct % JP : JP - 1, nq = ct < JP * NQ ? ct / JP : NQ - 1;   // spare lanes mimic the last unit lane
+        const int chunk = (fast2_rowoff(W, fast2_unit_at(JP, jp, m)) + 4 * nq) / 4;
+        if (chunk_of_group[chunk % 8] >= 0 && chunk_of_group[chunk % 8] != chunk) return false;
+        chunk_of_group[chunk % 8] = chunk;
+      }
+    }
+  return true;
+}
+static_assert(fast2_schedule_is_a_permutation(5) && fast2_schedule_is_a_permutation(8), "spare-row schedule must visit every unit once");
+static_assert(fast2_row_loads_conflict_free(10) && fast2_row_loads_conflict_free(16), "row shifts must keep the activation-quad loads conflict-free");
+
 // W = padded hidden width the kernel is compiled for; fast = layout of the specialised 1-W-W-1 tanh path
 __host__ __device__ constexpr SmallLayout make_layout(int W, int n_hidden, int in_dim, long long d, int fast = 0) {
   SmallLayout L{};
