@@ -153,6 +153,74 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_batched_kernel(GemmArgs g)
   }
 }
 
+// Products with a reduction of at most 8 terms (the wide BNN's first layer, in_dim = 1: z = x W^T + b over 100 000 rows x 512 units,
+// and the backward product through its output layer, K = out_dim = 1) are outer-product-like and memory-bound: one thread per
+// (row, 4 consecutive columns), 16-byte loads / stores where the operands allow.  The tiled SIMT kernel spent 1.7 / 1.2 ms per
+// evaluation on them writing 8 x 8 blocks with scalar stores (1.6 GB: 0.25 ms at HBM speed).  Same arithmetic in the same order
+// (fmaf over k ascending, tanhf) as sgemm_batched_kernel: bit-identical results.
+constexpr int SMALLK_MAX = 8;
+template <int EPI>
+__global__ void __launch_bounds__(256) smallk_gemm_kernel(GemmArgs g) {
+  const int b = blockIdx.y;
+  const int nq = (g.N + 3) / 4;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)g.M * nq) return;
+  const int m = (int)(t / nq), n = (int)(t % nq) * 4;
+  const float* __restrict__ A = g.A + (long long)b * g.a_bs + (long long)m * g.a_sm;
+  const float* __restrict__ B = g.B + (long long)b * g.b_bs + (long long)n * g.b_sn;
+  const int nv = g.N - n < 4 ? g.N - n : 4;
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const bool bvec = g.b_sn == 1 && nv == 4 && (g.b_sk & 3) == 0 && (g.b_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.B) & 15u) == 0);
+  for (int k = 0; k < g.K; ++k) {
+    const float av = __ldg(A + (long long)k * g.a_sk);
+    float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float* bk = B + (long long)k * g.b_sk;
+    if (bvec) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(bk));
+      bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nv) bv[j] = __ldg(bk + (long long)j * g.b_sn);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = fmaf(av, bv[j], acc[j]);
+  }
+  float aux[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (EPI == EPI_DACT) {
+    const float* ar = g.aux + (long long)b * g.aux_bs + (long long)m * g.ld_aux + n;
+    if (nv == 4 && (g.ld_aux & 3) == 0 && (g.aux_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15u) == 0)) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ar));
+      aux[0] = v.x; aux[1] = v.y; aux[2] = v.z; aux[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nv) aux[j] = __ldg(ar + j);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j >= nv) break;
+    float v = acc[j];
+    if (EPI == EPI_BIAS_ACT) {
+      v += __ldg(g.bias + (long long)b * g.bias_bs + n + j);
+      if (g.act == VIHMC_ACT_TANH) v = tanhf(v);
+      else if (g.act == VIHMC_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+    } else if (EPI == EPI_DACT) {
+      v *= (g.act == VIHMC_ACT_TANH) ? (1.0f - aux[j] * aux[j]) : (aux[j] > 0.0f ? 1.0f : 0.0f);
+    }
+    acc[j] = v;
+  }
+  float* cr = g.C + (long long)b * g.c_bs + (long long)m * g.ldc + n;
+  if (nv == 4 && (g.ldc & 3) == 0 && (g.c_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0)) {
+    *reinterpret_cast<float4*>(cr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) cr[j] = acc[j];
+  }
+}
+
 // VIHMC_DENSE_SIMT=1 keeps every GEMM on the FP32-SIMT kernel (A/B runs and the baseline the
 // tensor-core kernel is checked against)
 static bool tensor_cores_enabled() {
@@ -179,6 +247,15 @@ static int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st, float* scr
     t.B = g.A; t.b_bs = g.a_bs; t.b_sk = g.a_sk; t.b_sn = g.a_sm;
     t.M = g.N; t.N = 1; t.ldc = 1;
     if (tc_gemm_eligible(t)) return launch_tc_gemm<EPI>(t, batch, st, scratch);   // no fused row sums: opA is not dz any more
+  }
+  if (EPI != EPI_HEAD && force < 0 && g.K <= SMALLK_MAX && g.N >= 16) {
+    const long long threads = (long long)g.M * ((g.N + 3) / 4);
+    if ((threads + 255) / 256 < 0x7fffffffLL) {
+      dim3 sgrid((unsigned)((threads + 255) / 256), batch);
+      smallk_gemm_kernel<EPI><<<sgrid, 256, 0, st>>>(g);
+      VIHMC_LAUNCH_OK("smallk_gemm_kernel");
+      return VIHMC_OK;
+    }
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
   sgemm_batched_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
