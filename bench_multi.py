@@ -12,7 +12,7 @@ from __future__ import annotations
 import time
 
 CFG4_CHAINS_PER_GPU, CFG4_SAMPLES, CFG4_L, CFG4_EPS = 512, 5, 7, 1e-4   # BASELINE configs[3]: 4096 chains over 8 GPUs
-CFG5_CHAINS, CFG5_ROWS, CFG5_SAMPLES, CFG5_L, CFG5_EPS = 8, 100_000, 2, 4, 2e-6
+CFG5_CHAINS, CFG5_ROWS, CFG5_SAMPLES, CFG5_L, CFG5_EPS = 8, 100_000, 4, 4, 2e-6
 CFG5_GFLOP = 472.4          # per chain-grad-eval over all 100k rows
 
 
